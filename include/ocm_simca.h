@@ -1,0 +1,170 @@
+/*
+ * ocm_simca.h -- C ABI of the B200-native SIMCA / DD-SIMCA hot path (libocm_simca_b200.so).
+ *
+ * The reference (TEAM-AIOLY/OCM-VAE-SIMCA) is pure Python and has no FFI of its own
+ * (SURVEY.md §8(b)); its boundary for this path is the arithmetic that utils/SIMCA.py
+ * delegates to numpy / scikit-learn.  Each entry point below replaces one such call
+ * site (cited per function) and is what a ctypes / cffi / pybind stub on the reference
+ * side binds -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t on a CUDA failure or a
+ *     negative OCM_E* code on bad arguments; ocm_last_error() gives a thread-local message;
+ *   - all array pointers are DEVICE pointers unless the parameter name starts with h_;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - the caller owns every buffer; nothing is allocated, freed or synchronised inside
+ *     (exception: the *_host convenience calls at the end, which say so);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls on distinct streams / buffers are thread-safe.
+ */
+#ifndef OCM_SIMCA_H_
+#define OCM_SIMCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCM_ABI_VERSION 1
+
+#define OCM_EINVAL (-1)   /* bad argument (NULL pointer, non-positive size, unknown enum) */
+#define OCM_ELIMIT (-2)   /* size outside what the kernels support (e.g. n_components > 64) */
+#define OCM_EALIGN (-3)   /* pointer / leading dimension alignment not supported by this path */
+
+/* preprocessing modes */
+#define OCM_PRE_SNV       1   /* (x - mean_row) / (std_row(ddof=0) + eps)      simca_nuts.py:48-50 */
+#define OCM_PRE_CENTER    2   /* x - mu_col                                     sklearn PCA centring, SIMCA.py:64,:127 */
+#define OCM_PRE_AUTOSCALE 3   /* (x - mu_col) / sigma_col                       vae_model.py:124 */
+#define OCM_PRE_SNV_CENTER 4  /* SNV then column centring in one pass           */
+
+/* decision rules (utils/SIMCA.py:131-145) */
+#define OCM_RULE_SIM 0   /* max(a, b)        */
+#define OCM_RULE_ALT 1   /* sqrt(a^2 + b^2)  */
+#define OCM_RULE_CI  2   /* a + b            */
+#define OCM_RULE_DD  3   /* a + b with a = t2dof*T2/h0, b = qdof*Q/v0 (same arithmetic as CI) */
+
+int         ocm_abi_version(void);
+const char* ocm_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
+uint64_t    ocm_launch_count(void);
+
+/* ---- a1 / a2: streaming preprocessing ------------------------------------------------
+ * Y = pre(X).  mu / sigma are column vectors [p] (may be NULL where the mode does not use
+ * them).  In-place (Y == X, ldy == ldx) is allowed. */
+int ocm_preprocess_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_t mode,
+                       const float* mu, const float* sigma, float eps,
+                       float* Y, int64_t ldy, void* stream);
+
+/* ---- a2 / a4: column moments of selected rows -----------------------------------------
+ * colsum[j] += sum_r (x[r][j] - shift[j]),  colsumsq[j] += sum_r (x[r][j] - shift[j])^2 in fp64.
+ * row_idx (int64, may be NULL = rows 0..n-1) gathers rows; shift / colsumsq may be NULL.
+ * The outputs are ACCUMULATED into (zero them first). */
+int ocm_colstats_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                     const double* shift, double* colsum, double* colsumsq, void* stream);
+int ocm_colstats_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                     const double* shift, double* colsum, double* colsumsq, void* stream);
+
+/* ---- a4: partitioned Gram accumulation (replaces the SVD inside sklearn PCA.fit,
+ * utils/SIMCA.py:64-66,:75) ------------------------------------------------------------
+ * G[i][j] += sum_r (x[r][i]-shift[i]) (x[r][j]-shift[j]) for j >= i (UPPER triangle only),
+ * fp64 accumulation on the FP64 pipe.  G is p x p row-major with leading dimension p. */
+int ocm_gram_f64acc_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                        const double* shift, double* G, void* stream);
+int ocm_gram_f64acc_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                        const double* shift, double* G, void* stream);
+
+/* Combine per-partition moments into a covariance:  with weights w[g] in {0,1,...}
+ *   N = sum w_g n_g,  s = sum w_g colsum_g,  G = sum w_g G_g,  d = s/N,
+ *   mean = shift + d,  C = (G - N d d^T)/(N-1)  (full symmetric p x p written to C);
+ *   delta[p] (required scratch/output) receives d, mean[p] may be NULL.
+ * Gparts [ngroups][p][p] (upper triangles valid), sparts [ngroups][p], h_counts / h_weights
+ * are HOST arrays of length ngroups.  Used for plain fits (ngroups = 1), the multi-GPU
+ * all-reduced fit and CV folds (weight 0 on the held-out fold). */
+int ocm_cov_from_parts_f64(const double* Gparts, const double* sparts, const int64_t* h_counts,
+                           const double* h_weights, int32_t ngroups, int32_t p,
+                           const double* shift, double* C, double* mean, double* delta,
+                           void* stream);
+
+/* ---- a5 / a9 / a10: fused scoring (replaces pca.transform + inverse_transform + the
+ * two reductions of SIMCA.predict / SIMCA.transform, utils/SIMCA.py:101-145) -----------
+ * For each row x:  [optional SNV] -> xc = x - mu -> t = P xc -> r = xc - P^T t ->
+ *   T2 = t^T Sinv t,  Q = |r|^2,  a = T2*ct, b = Q*cq, d = rule(a,b), accept = d < dlim.
+ * P is [A][p] row-major (orthonormal rows), Sinv is [A][A] full symmetric.
+ * T2 / Q / accept / scores may each be NULL; scores [n][A] (the PCA scores t, exported only
+ * for the reference's `_model[cls]["T"]`) is off on the bulk path.  Only distances and
+ * decisions go back to HBM. */
+typedef struct {
+    int32_t A;          /* number of components (1..64) */
+    int32_t rule;       /* OCM_RULE_* */
+    int32_t snv;        /* 1: apply row SNV (eps below) before centring */
+    float   snv_eps;
+    float   ct, cq;     /* reduced-distance scales (1/T2_limit, 1/Q_limit; dof/scale for dd) */
+    float   dlim;       /* critical distance (strict <) */
+} ocm_score_params;
+
+int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                        const float* mu, const float* P, const float* Sinv,
+                        const ocm_score_params* h_params,
+                        float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
+int ocm_simca_score_f64in(const double* X, int64_t n, int32_t p, int64_t ldx,
+                          const double* mu, const float* P, const float* Sinv,
+                          const ocm_score_params* h_params,
+                          float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
+/* same contract, forced onto the FP32-pipe kernel (any shape; the dispatcher above picks the
+ * tcgen05 kernel when the shape allows it) */
+int ocm_simca_score_simt_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                             const float* mu, const float* P, const float* Sinv,
+                             const ocm_score_params* h_params,
+                             float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
+
+/* 1 when ocm_simca_score_f32 would take the tcgen05/TMA kernel for this shape (bulk path:
+ * fp32, p a multiple of the K-slice, 16-byte aligned rows), else 0. */
+int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+
+/* ---- a12: all nested models A = 1..Amax in one pass (CV grid, CVSIMCA.py:157-200) ------
+ * inv_eig[Amax] = 1/lambda_a (diagonal Sinv of a PCA model).  Outputs are [n][Amax]:
+ *   T2[i][A-1] = sum_{a<=A} t_a^2 inv_eig_a,  Q[i][A-1] = |r_Amax|^2 + sum_{a>A} t_a^2.
+ * ct / cq / dlim are per-A arrays [Amax] (device); accept may be NULL. */
+int ocm_simca_score_multiA_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                               const float* mu, const float* P, const float* inv_eig,
+                               int32_t Amax, int32_t rule, int32_t snv, float snv_eps,
+                               const float* ct, const float* cq, const float* dlim,
+                               float* T2, float* Q, uint8_t* accept, void* stream);
+int ocm_simca_score_multiA_f64in(const double* X, int64_t n, int32_t p, int64_t ldx,
+                                 const double* mu, const float* P, const float* inv_eig,
+                                 int32_t Amax, int32_t rule, int32_t snv, float snv_eps,
+                                 const float* ct, const float* cq, const float* dlim,
+                                 float* T2, float* Q, uint8_t* accept, void* stream);
+
+/* ---- a11 / f3: conformity counts on device (utils/SIMCA.py:238-266) --------------------
+ * counts[m][4] += {TP, TN, FP, FN} for each of the m decision columns of accept[n][m],
+ * is_target[n] = 1 where y_true == class_index. */
+int ocm_conformity_counts(const uint8_t* accept, const uint8_t* is_target, int64_t n, int32_t m,
+                          int64_t* counts, void* stream);
+
+/* ---- a14: VAE-SIMCA latent / reconstruction scoring (VAE_SIMCA.py:359-365,
+ * utils/final_vaesimca.py:479-492, vae_model.py:164) ------------------------------------
+ *   d2[i] = (z_i - m)^T Sinv (z_i - m)     z [n][d] fp32, Sinv [d][d] full symmetric
+ *   q[i]  = sum_j (x[i][j] - xrec[i][j])^2 x, xrec [n][p] (xrec fp32 or bf16)
+ * x / xrec may be NULL (then q is not written); z may be NULL (then d2 is not written). */
+int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_t ldz,
+                         const float* m, const float* Sinv,
+                         const float* x, const void* xrec, int32_t xrec_is_bf16,
+                         int32_t p, int64_t ldx, int64_t ldxrec,
+                         float* d2, float* q, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end call bench.py times as `e2e`) -------------
+ * Scores h_X (HOST, pageable or pinned) in row chunks, overlapping H2D copies with the
+ * kernel on two internal streams, and writes h_T2 / h_Q / h_accept (HOST).  Allocates and
+ * frees its own staging buffers and synchronises before returning. */
+int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, int64_t ldx,
+                             const float* h_mu, const float* h_P, const float* h_Sinv,
+                             const ocm_score_params* h_params, int64_t chunk_rows,
+                             float* h_T2, float* h_Q, uint8_t* h_accept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCM_SIMCA_H_ */

@@ -1,0 +1,223 @@
+// PCA-fit moments: column sums and the X^T X Gram of selected rows,
+// accumulated in fp64 on the FP64 pipe, plus the combination of per-partition moments
+// into a covariance.  This replaces the LAPACK SVD that sklearn's PCA runs inside
+// utils/SIMCA.py:64-66 / :75 -- the eigen-decomposition of the covariance gives the same
+// loadings and explained variances (S^2/(n-1)) without ever forming U.
+//
+// This is the exact path used for fits that fit in L2 (CV folds, config 1/2) where
+// accuracy, not throughput, is the constraint; the bulk config-4 path is the tensor-core
+// Gram in gram_tc.cu.  Rows are selected through an optional int64 gather index so CV
+// folds never materialise copies of X.
+#include "ocm_common.cuh"
+
+namespace ocm {
+
+// ---------------------------------------------------------------- column sums -----------
+// grid: (ceil(p/256), row_blocks); each thread owns one column, walks a strided set of rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colstats_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx,
+                int64_t n, int p, const double* __restrict__ shift,
+                double* __restrict__ colsum, double* __restrict__ colsumsq) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    const double sh = shift ? shift[j] : 0.0;
+    double s = 0.0, ss = 0.0;
+    for (int64_t r = blockIdx.y; r < n; r += gridDim.y) {
+        const int64_t row = row_idx ? row_idx[r] : r;
+        const double v = (double)X[row * ldx + j] - sh;
+        s += v;
+        ss = fma(v, v, ss);
+    }
+    atomicAdd(colsum + j, s);
+    if (colsumsq) atomicAdd(colsumsq + j, ss);
+}
+
+// ---------------------------------------------------------------- fp64 Gram -------------
+// 64x64 output tile per CTA (upper-triangle tiles only), 4x4 doubles per thread, K (rows)
+// split over gridDim.z with one fp64 atomicAdd per output element per split.
+constexpr int GT = 64;   // tile edge
+constexpr int GK = 16;   // rows per shared-memory stage
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gram_f64_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx,
+                int64_t n, int p, const double* __restrict__ shift, double* __restrict__ G,
+                int64_t rows_per_split) {
+    // map blockIdx.x to an upper-triangle tile (ti <= tj)
+    const int nt = (p + GT - 1) / GT;
+    int t = blockIdx.x, ti = 0;
+    while (t >= nt - ti) { t -= nt - ti; ++ti; }
+    const int tj = ti + t;
+    const int i0 = ti * GT, j0 = tj * GT;
+
+    __shared__ double As[GK][GT + 1];
+    __shared__ double Bs[GK][GT + 1];
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(n, r_begin + rows_per_split);
+
+    // loader mapping: 256 threads cover 16 rows x 64 cols in 4 steps of 4 rows
+    const int lc = threadIdx.x & 63, lr = threadIdx.x >> 6;
+    const double shA = (shift && i0 + lc < p) ? shift[i0 + lc] : 0.0;
+    const double shB = (shift && j0 + lc < p) ? shift[j0 + lc] : 0.0;
+
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += GK) {
+#pragma unroll
+        for (int s = 0; s < GK / 4; ++s) {
+            const int kk = lr + 4 * s;
+            const int64_t r = r0 + kk;
+            double a = 0.0, b = 0.0;
+            if (r < r_end) {
+                const int64_t row = row_idx ? row_idx[r] : r;
+                const T* xr = X + row * ldx;
+                if (i0 + lc < p) a = (double)xr[i0 + lc] - shA;
+                if (j0 + lc < p) b = (double)xr[j0 + lc] - shB;
+            }
+            As[kk][lc] = a;
+            Bs[kk][lc] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; b[u] = Bs[kk][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = i0 + ty * 4 + u;
+        if (i >= p) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int j = j0 + tx * 4 + v;
+            if (j < p && j >= i) atomicAdd(G + (int64_t)i * p + j, acc[u][v]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- combine ---------------
+struct PartsArgs {
+    int ngroups;
+    double weights[64];
+    double N;
+};
+
+__global__ void __launch_bounds__(256)
+mean_from_parts_kernel(const double* __restrict__ sparts, PartsArgs a, int p,
+                       const double* __restrict__ shift, double* __restrict__ delta,
+                       double* __restrict__ mean) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double s = 0.0;
+    for (int g = 0; g < a.ngroups; ++g)
+        if (a.weights[g] != 0.0) s += a.weights[g] * sparts[(int64_t)g * p + j];
+    const double d = s / a.N;
+    delta[j] = d;
+    if (mean) mean[j] = (shift ? shift[j] : 0.0) + d;
+}
+
+__global__ void __launch_bounds__(256)
+cov_from_parts_kernel(const double* __restrict__ Gparts, PartsArgs a, int p,
+                      const double* __restrict__ delta, double* __restrict__ C) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= p || j < i) return;
+    const int64_t pp = (int64_t)p * p;
+    double g = 0.0;
+    for (int k = 0; k < a.ngroups; ++k)
+        if (a.weights[k] != 0.0) g += a.weights[k] * Gparts[k * pp + (int64_t)i * p + j];
+    const double c = (g - a.N * delta[i] * delta[j]) / (a.N - 1.0);
+    C[(int64_t)i * p + j] = c;
+    C[(int64_t)j * p + i] = c;
+}
+
+template <typename T>
+int colstats_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                  const double* shift, double* colsum, double* colsumsq, void* stream) {
+    OCM_REQUIRE(X && colsum && n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    if (n == 0) return 0;
+    int64_t rb = (n + 63) / 64;
+    int64_t cap = (int64_t)sm_count() * 8 / ((p + 255) / 256) + 1;
+    if (rb > cap) rb = cap;
+    if (rb > 65535) rb = 65535;
+    dim3 grid((p + 255) / 256, (unsigned)rb);
+    colstats_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, row_idx, n, p, shift, colsum, colsumsq);
+    return check_launch("colstats_kernel");
+}
+
+template <typename T>
+int gram_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+              const double* shift, double* G, void* stream) {
+    OCM_REQUIRE(X && G && n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    if (n == 0) return 0;
+    const int nt = (p + GT - 1) / GT;
+    const int ntiles = nt * (nt + 1) / 2;
+    // enough K-splits to fill the machine ~2 waves, at least 64 rows per split
+    int64_t want = ((int64_t)sm_count() * 4 + ntiles - 1) / ntiles;
+    int64_t max_splits = (n + 63) / 64;
+    int64_t splits = want < 1 ? 1 : want;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 65535) splits = 65535;
+    int64_t rows_per_split = (n + splits - 1) / splits;
+    rows_per_split = (rows_per_split + GK - 1) / GK * GK;
+    splits = (n + rows_per_split - 1) / rows_per_split;
+    dim3 grid(ntiles, 1, (unsigned)splits);
+    gram_f64_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, row_idx, n, p, shift, G, rows_per_split);
+    return check_launch("gram_f64_kernel");
+}
+
+}  // namespace ocm
+
+extern "C" int ocm_colstats_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                const double* shift, double* colsum, double* colsumsq, void* stream) {
+    return ocm::colstats_impl<float>(X, ldx, row_idx, n, p, shift, colsum, colsumsq, stream);
+}
+extern "C" int ocm_colstats_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                const double* shift, double* colsum, double* colsumsq, void* stream) {
+    return ocm::colstats_impl<double>(X, ldx, row_idx, n, p, shift, colsum, colsumsq, stream);
+}
+extern "C" int ocm_gram_f64acc_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                   const double* shift, double* G, void* stream) {
+    return ocm::gram_impl<float>(X, ldx, row_idx, n, p, shift, G, stream);
+}
+extern "C" int ocm_gram_f64acc_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                   const double* shift, double* G, void* stream) {
+    return ocm::gram_impl<double>(X, ldx, row_idx, n, p, shift, G, stream);
+}
+
+extern "C" int ocm_cov_from_parts_f64(const double* Gparts, const double* sparts, const int64_t* h_counts,
+                                      const double* h_weights, int32_t ngroups, int32_t p,
+                                      const double* shift, double* C, double* mean, double* delta,
+                                      void* stream) {
+    using namespace ocm;
+    OCM_REQUIRE(Gparts && sparts && h_counts && C && delta && p > 0, OCM_EINVAL, "NULL buffer");
+    OCM_REQUIRE(ngroups >= 1 && ngroups <= 64, OCM_ELIMIT, "1..64 partitions supported");
+    PartsArgs a;
+    a.ngroups = ngroups;
+    a.N = 0.0;
+    for (int g = 0; g < ngroups; ++g) {
+        a.weights[g] = h_weights ? h_weights[g] : 1.0;
+        a.N += a.weights[g] * (double)h_counts[g];
+    }
+    OCM_REQUIRE(a.N >= 2.0, OCM_EINVAL, "need at least two rows");
+    mean_from_parts_kernel<<<(p + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sparts, a, p, shift, delta, mean);
+    int rc = check_launch("mean_from_parts_kernel");
+    if (rc) return rc;
+    dim3 grid((p + 255) / 256, p);
+    cov_from_parts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Gparts, a, p, delta, C);
+    return check_launch("cov_from_parts_kernel");
+}

@@ -1,0 +1,324 @@
+"""Device pipeline of the SIMCA hot path: thin Python over the C ABI (include/ocm_simca.h).
+
+torch is used for device memory, streams and (multi-GPU) torch.distributed only; every
+numerical step is a call into libocm_simca_b200.so.  Nothing here falls back to the CPU.
+
+    moments -> covariance -> eigh -> (mean, loadings, eigenvalues)      fit   (SIMCA.py:62-75)
+    fused score kernel -> T2, Q, accept                                 predict (SIMCA.py:120-154)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import native
+from .limits import RULES
+
+_PRE = {"snv": 1, "center": 2, "autoscale": 3, "snv_center": 4}
+
+
+def _torch():
+    return native.require_cuda()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(X, device=None, dtype=None):
+    """numpy / torch (any device) -> 2-D row-contiguous CUDA tensor, fp32 or fp64."""
+    torch = _torch()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(X, torch.Tensor):
+        t = X
+    else:
+        a = np.asarray(X)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    if dtype is not None:
+        t = t.to(dtype)
+    t = t.to(device, non_blocking=False)
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D array [n_samples, n_features]")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def index_tensor(idx, device):
+    torch = _torch()
+    if idx is None:
+        return None
+    if isinstance(idx, torch.Tensor):
+        return idx.to(device=device, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.asarray(idx, dtype=np.int64), device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# preprocessing
+# ------------------------------------------------------------------------------------------
+def preprocess(X, mode, mu=None, sigma=None, eps=1e-8, out=None):
+    """SNV / centre / autoscale / SNV+centre on fp32 device rows (ocm_preprocess_f32)."""
+    torch = _torch()
+    X = to_device(X, dtype=torch.float32)
+    if out is None:
+        out = torch.empty_like(X)
+    mu_t = None if mu is None else to_device(torch.as_tensor(mu).reshape(1, -1), X.device, torch.float32)
+    sg_t = None if sigma is None else to_device(torch.as_tensor(sigma).reshape(1, -1), X.device, torch.float32)
+    rc = native.lib().ocm_preprocess_f32(_p(X), X.shape[0], X.shape[1], X.stride(0), _PRE[mode], _p(mu_t),
+                                         _p(sg_t), float(eps), _p(out), out.stride(0), _stream())
+    native.check(rc, "ocm_preprocess_f32")
+    return out
+
+
+def snv(X, eps=1e-8):
+    return preprocess(X, "snv", eps=eps)
+
+
+# ------------------------------------------------------------------------------------------
+# PCA fit: moments -> covariance -> eigh
+# ------------------------------------------------------------------------------------------
+def colstats(X, row_idx=None, shift=None, want_sq=False):
+    torch = _torch()
+    n = X.shape[0] if row_idx is None else row_idx.numel()
+    p = X.shape[1]
+    s = torch.zeros(p, dtype=torch.float64, device=X.device)
+    ss = torch.zeros(p, dtype=torch.float64, device=X.device) if want_sq else None
+    fn = native.lib().ocm_colstats_f32 if X.dtype == torch.float32 else native.lib().ocm_colstats_f64
+    native.check(fn(_p(X), X.stride(0), _p(row_idx), n, p, _p(shift), _p(s), _p(ss), _stream()), "ocm_colstats")
+    return s, ss, n
+
+
+def gram(X, row_idx=None, shift=None, out=None):
+    """Upper triangle of sum_r (x_r - shift)(x_r - shift)^T, fp64 accumulation."""
+    torch = _torch()
+    n = X.shape[0] if row_idx is None else row_idx.numel()
+    p = X.shape[1]
+    if out is None:
+        out = torch.zeros((p, p), dtype=torch.float64, device=X.device)
+    fn = native.lib().ocm_gram_f64acc_f32 if X.dtype == torch.float32 else native.lib().ocm_gram_f64acc_f64
+    native.check(fn(_p(X), X.stride(0), _p(row_idx), n, p, _p(shift), _p(out), _stream()), "ocm_gram_f64acc")
+    return out
+
+
+def cov_from_parts(Gparts, sparts, counts, weights, shift):
+    """Combine partition moments into (C [p,p] full symmetric, mean [p]) -- ocm_cov_from_parts_f64."""
+    torch = _torch()
+    ng, p = sparts.shape
+    Cm = torch.empty((p, p), dtype=torch.float64, device=sparts.device)
+    mean = torch.empty(p, dtype=torch.float64, device=sparts.device)
+    delta = torch.empty(p, dtype=torch.float64, device=sparts.device)
+    cnt = (C.c_int64 * ng)(*[int(c) for c in counts])
+    wts = (C.c_double * ng)(*[float(w) for w in weights])
+    rc = native.lib().ocm_cov_from_parts_f64(_p(Gparts), _p(sparts), cnt, wts, ng, p, _p(shift), _p(Cm),
+                                             _p(mean), _p(delta), _stream())
+    native.check(rc, "ocm_cov_from_parts_f64")
+    return Cm, mean
+
+
+def covariance(X, row_idx=None, group=None):
+    """Sample covariance (ddof=1) and column mean of the selected rows.
+
+    Two passes (both tiny next to scoring): column sums give a provisional mean that is
+    used as the shift of the Gram accumulation, so G - n*d*d^T never cancels.
+    With torch.distributed initialised and `group` given, the partial moments of the row
+    shards are all-reduced (NCCL over NVLink) before the combination."""
+    torch = _torch()
+    s0, _, n = colstats(X, row_idx)
+    n_tot = torch.tensor([float(n)], dtype=torch.float64, device=X.device)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(s0, group=group)
+        dist.all_reduce(n_tot, group=group)
+    shift = s0 / n_tot
+    G = gram(X, row_idx, shift)
+    s1, _, _ = colstats(X, row_idx, shift)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(G, group=group)
+        dist.all_reduce(s1, group=group)
+    N = int(round(float(n_tot.item())))
+    Cm, mean = cov_from_parts(G.unsqueeze(0), s1.unsqueeze(0), [N], [1.0], shift)
+    return Cm, mean, N
+
+
+def sign_normalise_(V):
+    """sklearn svd_flip(u_based_decision=False): the largest-|entry| of each row positive."""
+    torch = _torch()
+    idx = V.abs().argmax(dim=1, keepdim=True)
+    sgn = torch.sign(torch.gather(V, 1, idx))
+    sgn[sgn == 0] = 1
+    V.mul_(sgn)
+    return V
+
+
+def eigh_topk(Cm, k):
+    """All eigenvalues (descending) and the k leading eigenvectors (rows) of a symmetric fp64
+    matrix, on the device."""
+    torch = _torch()
+    lib = native.lib()
+    if hasattr(lib, "ocm_eigh_topk_f64") and getattr(lib.ocm_eigh_topk_f64, "argtypes", None):
+        p = Cm.shape[-1]
+        batch = 1 if Cm.dim() == 2 else Cm.shape[0]
+        evals = torch.empty((batch, p), dtype=torch.float64, device=Cm.device)
+        evecs = torch.empty((batch, k, p), dtype=torch.float64, device=Cm.device)
+        wb = int(lib.ocm_eigh_work_bytes(p, k, batch))
+        work = torch.empty(wb, dtype=torch.uint8, device=Cm.device)
+        A = Cm.clone()
+        native.check(lib.ocm_eigh_topk_f64(_p(A), p, k, batch, _p(evals), _p(evecs), _p(work), wb, _stream()),
+                     "ocm_eigh_topk_f64")
+        if Cm.dim() == 2:
+            return evals[0], evecs[0]
+        return evals, evecs
+    w, V = torch.linalg.eigh(Cm)
+    w = torch.flip(w, dims=[-1])
+    V = torch.flip(V, dims=[-1])[..., :k].transpose(-1, -2).contiguous()
+    if V.dim() == 2:
+        sign_normalise_(V)
+    else:
+        for b in range(V.shape[0]):
+            sign_normalise_(V[b])
+    return w, V
+
+
+@dataclass
+class PCAModel:
+    """Device-resident PCA of one class: everything predict needs, plus what the reference
+    exposes under `_model[cls]` (SIMCA.py:83-99)."""
+    mean: "object"        # torch f64 [p]
+    P: "object"           # torch f64 [A, p]  (rows sign-normalised)
+    eigs_all: np.ndarray  # host f64 [min(n, p)]  explained variances, descending
+    n_samples: int
+
+    def arrays32(self):
+        torch = _torch()
+        return self.mean.to(torch.float32), self.P.to(torch.float32).contiguous()
+
+
+def fit_pca(X, row_idx=None, k=2, group=None) -> PCAModel:
+    Cm, mean, n = covariance(X, row_idx, group)
+    p = X.shape[1]
+    evals, evecs = eigh_topk(Cm, k)
+    m = min(n, p)
+    eigs = evals[:m].clamp_min(0.0).cpu().numpy()
+    if n <= p:
+        eigs[n - 1:] = 0.0     # rank n-1: the reference's trailing values are ~1e-30 noise
+    return PCAModel(mean=mean, P=evecs, eigs_all=eigs, n_samples=n)
+
+
+# ------------------------------------------------------------------------------------------
+# fused scoring
+# ------------------------------------------------------------------------------------------
+def score(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=False, snv_eps=1e-8,
+          want_scores=False, force_simt=False):
+    """Fused T2 / Q / accept for the rows of X against one model.
+
+    X: CUDA tensor [n,p] fp32 or fp64.  mean [p], P [A,p], Sinv [A,A] any float dtype on the
+    device.  Returns (T2, Q, accept[, scores]) as device tensors (fp32, fp32, uint8[, fp32])."""
+    torch = _torch()
+    lib = native.lib()
+    n, p = X.shape
+    A = P.shape[0]
+    dev = X.device
+    T2 = torch.empty(n, dtype=torch.float32, device=dev)
+    Q = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = torch.empty(n, dtype=torch.uint8, device=dev)
+    sc = torch.empty((n, A), dtype=torch.float32, device=dev) if want_scores else None
+    prm = native.ScoreParams(A=A, rule=RULES[rule] if isinstance(rule, str) else int(rule), snv=int(bool(snv)),
+                             snv_eps=float(snv_eps), ct=float(ct), cq=float(cq), dlim=float(dlim))
+    P32 = P.to(torch.float32).contiguous()
+    S32 = Sinv.to(torch.float32).contiguous()
+    if X.dtype == torch.float64:
+        mu = mean.to(torch.float64).contiguous()
+        rc = lib.ocm_simca_score_f64in(_p(X), n, p, X.stride(0), _p(mu), _p(P32), _p(S32), C.byref(prm),
+                                       _p(T2), _p(Q), _p(acc), _p(sc), _stream())
+    else:
+        mu = mean.to(torch.float32).contiguous()
+        fn = lib.ocm_simca_score_simt_f32 if force_simt else lib.ocm_simca_score_f32
+        rc = fn(_p(X), n, p, X.stride(0), _p(mu), _p(P32), _p(S32), C.byref(prm), _p(T2), _p(Q), _p(acc),
+                _p(sc), _stream())
+    native.check(rc, "ocm_simca_score")
+    return (T2, Q, acc, sc) if want_scores else (T2, Q, acc)
+
+
+def score_multiA(X, mean, P, inv_eig, rule="alt", ct=None, cq=None, dlim=None, snv=False, snv_eps=1e-8):
+    """All nested models A = 1..Amax at once.  Returns T2, Q [n,Amax] fp32 and accept [n,Amax] uint8
+    (accept is None when no limits are given)."""
+    torch = _torch()
+    lib = native.lib()
+    n, p = X.shape
+    Amax = P.shape[0]
+    dev = X.device
+    T2 = torch.empty((n, Amax), dtype=torch.float32, device=dev)
+    Q = torch.empty((n, Amax), dtype=torch.float32, device=dev)
+    have_lim = ct is not None
+    acc = torch.empty((n, Amax), dtype=torch.uint8, device=dev) if have_lim else None
+    f32 = lambda v: None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float32), device=dev) \
+        if not isinstance(v, torch.Tensor) else v.to(device=dev, dtype=torch.float32).contiguous()
+    ct_t, cq_t, dl_t = f32(ct), f32(cq), f32(dlim)
+    P32 = P.to(torch.float32).contiguous()
+    ie = inv_eig.to(torch.float32).contiguous()
+    r = RULES[rule] if isinstance(rule, str) else int(rule)
+    if X.dtype == torch.float64:
+        mu = mean.to(torch.float64).contiguous()
+        fn = lib.ocm_simca_score_multiA_f64in
+    else:
+        mu = mean.to(torch.float32).contiguous()
+        fn = lib.ocm_simca_score_multiA_f32
+    rc = fn(_p(X), n, p, X.stride(0), _p(mu), _p(P32), _p(ie), Amax, r, int(bool(snv)), float(snv_eps),
+            _p(ct_t), _p(cq_t), _p(dl_t), _p(T2), _p(Q), _p(acc), _stream())
+    native.check(rc, "ocm_simca_score_multiA")
+    return T2, Q, acc
+
+
+def conformity_counts(accept, is_target):
+    """[m,4] int64 {TP,TN,FP,FN} per decision column (ocm_conformity_counts)."""
+    torch = _torch()
+    if accept.dim() == 1:
+        accept = accept.unsqueeze(1)
+    accept = accept.contiguous()
+    n, m = accept.shape
+    counts = torch.zeros((m, 4), dtype=torch.int64, device=accept.device)
+    tgt = is_target.to(device=accept.device, dtype=torch.uint8).contiguous()
+    native.check(native.lib().ocm_conformity_counts(_p(accept), _p(tgt), n, m, _p(counts), _stream()),
+                 "ocm_conformity_counts")
+    return counts
+
+
+def latent_score(z=None, m=None, Sinv=None, x=None, xrec=None):
+    """VAE-SIMCA epilogue: d2 = (z-m)^T Sinv (z-m), q = |x - xrec|^2 (ocm_latent_score_f32)."""
+    torch = _torch()
+    ref = z if z is not None else x
+    n, dev = ref.shape[0], ref.device
+    d2 = torch.empty(n, dtype=torch.float32, device=dev) if z is not None else None
+    q = torch.empty(n, dtype=torch.float32, device=dev) if x is not None else None
+    is_bf16 = 0
+    if z is not None:
+        z = z.to(torch.float32).contiguous()
+        m = m.to(device=dev, dtype=torch.float32).contiguous()
+        Sinv = Sinv.to(device=dev, dtype=torch.float32).contiguous()
+    if x is not None:
+        x = x.to(torch.float32).contiguous()
+        if xrec.dtype == torch.bfloat16:
+            is_bf16 = 1
+            xrec = xrec.contiguous()
+        else:
+            xrec = xrec.to(torch.float32).contiguous()
+    rc = native.lib().ocm_latent_score_f32(
+        _p(z), n, 0 if z is None else z.shape[1], 0 if z is None else z.stride(0), _p(m), _p(Sinv),
+        _p(x), _p(xrec), is_bf16, 0 if x is None else x.shape[1], 0 if x is None else x.stride(0),
+        0 if x is None else xrec.stride(0), _p(d2), _p(q), _stream())
+    native.check(rc, "ocm_latent_score_f32")
+    return d2, q

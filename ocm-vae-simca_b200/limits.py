@@ -1,0 +1,128 @@
+"""Critical limits of a SIMCA model: O(1) host arithmetic per model.
+
+These need special functions (F / chi-square quantiles with non-integer dof, erfinv) and
+run once per fitted model on scalars that the device produced: (n, A), the eigenvalue
+spectrum, and -- only for 'perc' / 'chi2pom' -- the training T2 / Q vectors.  The bulk
+work (T2, Q of every row) never comes through here.
+
+Behaviour follows /root/reference/utils/SIMCA.py:156-236 (cited per function).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import lru_cache
+from typing import Optional
+
+import numpy as np
+from scipy import stats
+from scipy.special import erfinv
+
+RULES = {"sim": 0, "alt": 1, "ci": 2, "dd": 3}
+
+
+@lru_cache(maxsize=4096)
+def _f_ppf(cl, d1, d2):
+    return float(stats.f.ppf(cl, d1, d2))
+
+
+@lru_cache(maxsize=4096)
+def _chi2_ppf(cl, dof):
+    return float(stats.chi2.ppf(cl, dof))
+
+
+T2_KINDS = ("perc", "Fdistrig", "Fdist", "chi2", "chi2pom")
+Q_KINDS = ("perc", "jm", "chi2box", "chi2pom")
+
+
+@dataclass
+class Limits:
+    T2_limit: float
+    Q_limit: float
+    D_limit: float
+    t2dof: Optional[int] = None
+    t2scale: Optional[float] = None
+    qdof: Optional[int] = None
+    qscale: Optional[float] = None
+
+    def reduced_scales(self, rule: str):
+        """(ct, cq) such that the reduced distances are T2*ct and Q*cq (SIMCA.py:131-144)."""
+        if rule == "dd":
+            return self.t2dof / self.t2scale, self.qdof / self.qscale
+        return 1.0 / self.T2_limit, 1.0 / self.Q_limit
+
+
+def tail_moments(eigs_all, A):
+    """theta_i = sum_{k>A} lambda_k^i, i=1..3 (SIMCA.py:189-191)."""
+    tail = np.asarray(eigs_all, dtype=np.float64)[A:]
+    return float(tail.sum()), float((tail ** 2).sum()), float((tail ** 3).sum())
+
+
+def hotelling_limit(kind, cl, A, n, T2=None):
+    """SIMCA.py:156-182.  Returns (limit, dof, scale); dof/scale only for 'chi2pom'."""
+    if kind == "Fdist":
+        return A * (n - 1) / (n - A) * _f_ppf(cl, A, n - A), None, None
+    if kind == "Fdistrig":
+        return (A / n) * (n ** 2 - 1) / (n - A) * _f_ppf(cl, A, n - A), None, None
+    if kind == "chi2":
+        return _chi2_ppf(cl, A), None, None
+    if kind == "perc":
+        return float(np.percentile(T2, cl * 100)), None, None
+    if kind == "chi2pom":
+        h0 = float(np.mean(T2))
+        var = float(np.var(T2, ddof=1)) if len(T2) > 1 else 0.0
+        dof = max(int(np.round(2 * h0 * h0 / var)) if var > 0 else 1, 1)
+        return h0 * _chi2_ppf(cl, dof) / dof, dof, h0
+    raise ValueError(f"unknown t2lim {kind!r}")
+
+
+def residual_limit(kind, cl, thetas, Q=None, verbose=False):
+    """SIMCA.py:184-217.  Returns (limit, dof, scale)."""
+    th1, th2, th3 = thetas
+    if kind == "jm":
+        # Jackson-Mudholkar
+        h0 = max(1.0 - (2.0 * th1 * th3) / (3.0 * th2 * th2), 0.001)
+        ca = np.sqrt(2.0) * erfinv(2.0 * cl - 1.0)
+        term = ca * np.sqrt(2.0 * th2 * h0 * h0) / th1 + 1.0 + th2 * h0 * (h0 - 1.0) / (th1 * th1)
+        return float(th1 * term ** (1.0 / h0)), None, None
+    if kind == "chi2box":
+        g, Ng = th2 / th1, th1 * th1 / th2
+        if verbose:  # the reference prints these unconditionally (SIMCA.py:207-208)
+            print("here we are")
+            print(th1, th2, g, Ng)
+        return float(g * stats.chi2.ppf(cl, Ng)), None, None
+    if kind == "perc":
+        return float(np.percentile(Q, cl * 100)), None, None
+    if kind == "chi2pom":
+        v0 = float(np.mean(Q))
+        dof = max(round(2 * v0 * v0 / float(np.var(Q, ddof=1))), 1)
+        return v0 * _chi2_ppf(cl, dof) / dof, dof, v0
+    raise ValueError(f"unknown qlim {kind!r}")
+
+
+def distance_limit(rule, dcl, A, t2lim, qlim, thetas, t2dof=None, qdof=None):
+    """SIMCA.py:219-236."""
+    if rule == "sim":
+        return 1
+    if rule == "alt":
+        return float(np.sqrt(2))
+    if rule == "ci":
+        th1, th2, _ = thetas
+        tr1 = A / t2lim + th1 / qlim
+        tr2 = A / t2lim ** 2 + th2 / qlim ** 2
+        return float((tr2 / tr1) * stats.chi2.ppf(dcl, tr1 * tr1 / tr2))
+    if rule == "dd":
+        return float(stats.chi2.ppf(dcl, t2dof + qdof))
+    raise ValueError(f"unknown type {rule!r}")
+
+
+def needs_training_scores(t2_kind, q_kind):
+    return t2_kind in ("perc", "chi2pom") or q_kind in ("perc", "chi2pom")
+
+
+def all_limits(rule, t2_kind, t2cl, q_kind, qcl, dcl, A, n, eigs_all, T2=None, Q=None,
+               verbose=False) -> Limits:
+    th = tail_moments(eigs_all, A)
+    tl, tdof, tsc = hotelling_limit(t2_kind, t2cl, A, n, T2)
+    ql, qdof, qsc = residual_limit(q_kind, qcl, th, Q, verbose=verbose)
+    dl = distance_limit(rule, dcl, A, tl, ql, th, tdof, qdof)
+    return Limits(float(tl), float(ql), dl, tdof, tsc, qdof, qsc)

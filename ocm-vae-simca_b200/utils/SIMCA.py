@@ -1,0 +1,264 @@
+"""SIMCA / DD-SIMCA one-class estimator -- drop-in for /root/reference/utils/SIMCA.py.
+
+Same constructor, same `fit / predict / transform / score / _metrics_simca_conformity`,
+same `_model[cls]` dictionary keys, same prints, same sklearn estimator behaviour
+(`clone`, `get_params/set_params`, last step of a `Pipeline`).  What differs is where the
+arithmetic runs: the PCA fit is a fp64 Gram accumulation + symmetric eigensolve on the
+GPU and predict/transform is ONE fused CUDA kernel per call that reads each spectrum once
+and writes back only T2, Q and the decision (engine.py -> include/ocm_simca.h).
+
+Deliberate deviations from the reference (each documented in DESIGN.md):
+  * n_components == 1 works (the reference crashes in np.cov, SIMCA.py:69);
+  * the predict-time decomposition IS the fit-time one (the reference refits a second,
+    randomized-SVD PCA, SIMCA.py:75 -- identical up to its own run-to-run noise);
+  * `invcovT` is exactly diag(1/lambda_a) (the reference's pinv(cov(T)) equals it to 1e-15);
+  * CUDA tensors are accepted and, for them, results stay on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+from sklearn.base import BaseEstimator, ClassifierMixin
+
+from .. import engine, limits
+
+
+class _DevicePCA:
+    """What `_model[cls]["pca_model"]` exposes: the sklearn-PCA attributes the reference's
+    callers touch (`components_`, `mean_`, `explained_variance_`, `n_components_`) plus
+    transform / inverse_transform for plotting code.  Host copies are made lazily."""
+
+    def __init__(self, pca: engine.PCAModel):
+        self._pca = pca
+        self.n_components_ = int(pca.P.shape[0])
+        self.n_samples_ = pca.n_samples
+        self.explained_variance_ = pca.eigs_all[: self.n_components_].copy()
+        self._P = self._mean = None
+
+    @property
+    def components_(self):
+        if self._P is None:
+            self._P = self._pca.P.cpu().numpy()
+        return self._P
+
+    @property
+    def mean_(self):
+        if self._mean is None:
+            self._mean = self._pca.mean.cpu().numpy()
+        return self._mean
+
+    def transform(self, X):
+        return (np.asarray(X) - self.mean_) @ self.components_.T
+
+    def inverse_transform(self, T):
+        return np.asarray(T) @ self.components_ + self.mean_
+
+
+class SIMCA(BaseEstimator, ClassifierMixin):
+    def __init__(self, n_components=2, model_class=None, type: str = 'alt', t2lim='Fdist', t2cl=0.95,
+                 qlim='jm', qcl=0.95, dcl=0.95, maxPC=20, criteria='compl', verbose=True):
+        self.n_components = n_components
+        self.model_class = model_class
+        self.type = type
+        self.t2lim = t2lim
+        self.t2cl = t2cl
+        self.qlim = qlim
+        self.qcl = qcl
+        self.criteria = criteria
+        self.dcl = dcl
+        self.maxPC = maxPC
+        self.metrics = {}
+        self.verbose = verbose
+
+    # ------------------------------------------------------------------ fit ------------
+    def fit(self, X, classes):
+        # argument normalisation mutates the constructor parameters exactly like the
+        # reference does (SIMCA.py:29-48); CVSIMCA relies on clone() before each fit.
+        classes_np = classes.detach().cpu().numpy() if hasattr(classes, "detach") else np.asarray(classes)
+        if self.model_class is None:
+            self.model_class = np.unique(classes_np)
+        elif isinstance(self.model_class, (int, np.integer)):
+            self.model_class = [self.model_class]
+        if not isinstance(self.n_components, list):
+            self.n_components = [self.n_components]
+        if len(self.n_components) == 1:
+            self.n_components = [self.n_components[0]] * len(self.model_class)
+        elif len(self.n_components) != len(self.model_class):
+            raise ValueError("n_components length must match number of classes")
+        if self.type == 'dd' and self.t2lim != 'chi2pom':
+            print('t2lim set as chi2pom')
+            self.t2lim = 'chi2pom'
+        if self.type == 'dd' and self.qlim != 'chi2pom':
+            print('qlim set as chi2pom')
+            self.qlim = 'chi2pom'
+
+        Xd = engine.to_device(X)
+        self._model = {}
+        for i, cls in enumerate(self.model_class):
+            rows = np.flatnonzero(classes_np == cls)
+            self._model[cls] = self._fit_one_class(Xd, rows, int(self.n_components[i]))
+        self.n_features_in_ = Xd.shape[1]
+        self.is_fitted_ = True
+        return self
+
+    def _fit_one_class(self, Xd, rows, A):
+        """Device restatement of SIMCA.py:62-99."""
+        idx = engine.index_tensor(rows, Xd.device)
+        n = int(idx.numel())
+        if not 1 <= A <= min(n - 1, Xd.shape[1], 64):
+            raise ValueError(f"n_components={A} must be in 1..min(n_class-1, n_features, 64)")
+        pca = engine.fit_pca(Xd, idx, A)
+        lam = pca.eigs_all[:A]
+        torch = engine._torch()
+        inv_eig = torch.as_tensor(1.0 / lam, device=Xd.device)
+        Sinv = torch.diag(inv_eig)
+        Xcls = Xd.index_select(0, idx)
+        T2, Q, _, T = engine.score(Xcls, pca.mean, pca.P, Sinv, want_scores=True)
+        T2h = T2.double().cpu().numpy()
+        Qh = Q.double().cpu().numpy()
+        lim = limits.all_limits(self.type, self.t2lim, self.t2cl, self.qlim, self.qcl, self.dcl, A, n,
+                                pca.eigs_all, T2h, Qh, verbose=True)
+        if self.type == 'dd':
+            # the reference keeps these on the instance (last class wins, SIMCA.py:179-180,:215-216)
+            self._t2dof, self._t2scfact = lim.t2dof, lim.t2scale
+            self._qdof, self._qscfact = lim.qdof, lim.qscale
+            T2red, Qred = lim.t2dof * T2h / lim.t2scale, lim.qdof * Qh / lim.qscale
+        else:
+            if self.t2lim == 'chi2pom':
+                self._t2dof, self._t2scfact = lim.t2dof, lim.t2scale
+            if self.qlim == 'chi2pom':
+                self._qdof, self._qscfact = lim.qdof, lim.qscale
+            T2red, Qred = T2h / lim.T2_limit, Qh / lim.Q_limit
+        return {
+            "pca_model": _DevicePCA(pca),
+            "n_components": A,
+            "xmean": pca.mean.cpu().numpy(),
+            "invcovT": np.diag(1.0 / lam),
+            "eigs_all": pca.eigs_all,
+            "T": T.double().cpu().numpy(),
+            "P": pca.P.cpu().numpy(),
+            "T2": T2h,
+            "Q": Qh,
+            "T2red": T2red,
+            "Qred": Qred,
+            "T2_limit": lim.T2_limit,
+            "Q_limit": lim.Q_limit,
+            "D_limit": lim.D_limit,
+            "n_samples": n,
+            # device-side handles (not in the reference)
+            "_pca": pca,
+            "_Sinv": Sinv,
+            "_limits": lim,
+        }
+
+    # ------------------------------------------------------------------ scoring ---------
+    def _score_class(self, Xd, cls, snv=False):
+        info = self._model[cls]
+        lim = info["_limits"]
+        ct, cq = lim.reduced_scales(self.type)
+        return engine.score(Xd, info["_pca"].mean, info["_pca"].P, info["_Sinv"], rule=self.type,
+                            ct=ct, cq=cq, dlim=lim.D_limit, snv=snv)
+
+    def transform(self, X):
+        """(T2, T2red, Q, Qred) of the LAST model class, as the reference returns (SIMCA.py:101-117)."""
+        on_device = _is_cuda_tensor(X)
+        Xd = engine.to_device(X)
+        for cls in self.model_class:
+            T2, Q, _ = self._score_class(Xd, cls)
+            lim = self._model[cls]["_limits"]
+            ct, cq = lim.reduced_scales(self.type)
+            T2red, Qred = T2 * ct, Q * cq
+        if on_device:
+            return T2, T2red, Q, Qred
+        f = lambda t: t.double().cpu().numpy()
+        T2h, Qh = f(T2), f(Q)
+        return T2h, T2h * ct, Qh, Qh * cq
+
+    def predict(self, X, y_true=None):
+        """0./1. acceptance per model class, shape [N, n_classes] (SIMCA.py:120-154)."""
+        on_device = _is_cuda_tensor(X)
+        Xd = engine.to_device(X)
+        torch = engine._torch()
+        out = torch.empty((Xd.shape[0], len(self.model_class)), dtype=torch.float64, device=Xd.device)
+        for i, cls in enumerate(self.model_class):
+            _, _, acc = self._score_class(Xd, cls)
+            out[:, i] = acc
+        predictions = out if on_device else out.cpu().numpy()
+        if y_true is not None:
+            yt = y_true.detach().cpu().numpy() if hasattr(y_true, "detach") else np.asarray(y_true)
+            pr = out.cpu().numpy() if on_device else predictions
+            for i, cls in enumerate(self.model_class):
+                self.metrics[cls] = self._metrics_simca_conformity(yt, pr[:, i], cls)
+                if self.verbose:
+                    m = self.metrics[cls]
+                    print(f"Sample class {cls} = {np.sum(yt == cls)}")
+                    print(f"Confusion Matrix for class {cls}:\nTP: {m['TP']}, TN: {m['TN']}, FP: {m['FP']}, FN: {m['FN']}")
+                    print(f"Class {cls} - Sensitivity: {m['sensitivity']}, Specificity: {m['specificity']:.4f}, "
+                          f"Accuracy: {m['accuracy']:.4f}, Efficiency: {m['efficiency']:.4f}")
+        return predictions
+
+    # ------------------------------------------------------------------ metrics ---------
+    def _metrics_simca_conformity(self, y_true, y_pred, class_index):
+        """Confusion counts and percentages (SIMCA.py:238-266); integer arithmetic on the host
+        (the on-device variant for the CV grid is engine.conformity_counts)."""
+        y_true = np.asarray(y_true)
+        y_pred = np.asarray(y_pred)
+        true_class = (y_true == class_index).astype(int)
+        TP = np.sum((y_pred == 1) & (true_class == 1))
+        TN = np.sum((y_pred == 0) & (true_class == 0))
+        FP = np.sum((y_pred == 1) & (true_class == 0))
+        FN = np.sum((y_pred == 0) & (true_class == 1))
+        sensitivity = TP / (TP + FN) * 100
+        specificity = TN / (TN + FP) * 100
+        accuracy = (TP + TN) / (TP + TN + FP + FN) * 100
+        efficiency = np.sqrt(sensitivity * specificity)
+        return {'sensitivity': sensitivity, 'specificity': specificity, 'accuracy': accuracy,
+                'efficiency': efficiency, 'TP': TP, 'TN': TN, 'FP': FP, 'FN': FN}
+
+    def score(self, X, y):
+        """Specificity of the prediction, as in the reference (SIMCA.py:268-278).  The
+        reference broadcasts (N,1) predictions against (N,) labels; here the single
+        model class is compared column-wise, which is what that code intends."""
+        y_pred = self.predict(X, y_true=y)
+        y_pred = y_pred.cpu().numpy() if _is_cuda_tensor(y_pred) else y_pred
+        cls = self.model_class[0] if len(self.model_class) == 1 else self.model_class
+        return self._metrics_simca_conformity(np.asarray(y), y_pred[:, 0], cls)['specificity']
+
+    # ------------------------------------------------------------------ plots -----------
+    def toplotT2Q(self, X, y_test):
+        """T2red-vs-Qred acceptance plot (SIMCA.py:280-307); needs matplotlib."""
+        import matplotlib.pyplot as plt
+        for cls in self._model:
+            _, T2red, _, Qred = self.transform(X)
+            Dlim = self._model[cls]['D_limit']
+            a = np.arange(0, Dlim + 0.0001, 0.0001)
+            plt.figure(figsize=(6, 6))
+            sc = plt.scatter(T2red, Qred, c=y_test, cmap='viridis', s=40, edgecolor='k', linewidth=0.5, alpha=0.7)
+            plt.plot(a, np.sqrt(np.maximum(Dlim ** 2 - a ** 2, 0)), 'b-', lw=2, label=f'class {cls} limit')
+            plt.xlabel(r"$T^2_{red}$"); plt.ylabel(r"$Q_{red}$")
+            plt.legend(*sc.legend_elements(), title="Class")
+            plt.xlim(left=0); plt.ylim(bottom=0); plt.grid(True, alpha=0.3); plt.tight_layout()
+            plt.show()
+            return plt
+
+    def toplotT2Q_iterative(self, X, y_test):
+        """Plotly version of the acceptance plot (SIMCA.py:310-381); needs plotly."""
+        import plotly.graph_objects as go
+        figs = []
+        labels = np.asarray(y_test).astype(str)
+        for cls in self._model:
+            _, T2red, _, Qred = self.transform(X)
+            Dlim = float(self._model[cls]['D_limit'])
+            a = np.linspace(0, Dlim, 1200)
+            fig = go.Figure()
+            for c in np.unique(labels):
+                mk = labels == c
+                fig.add_trace(go.Scatter(x=T2red[mk], y=Qred[mk], mode='markers', name=f"Class {c}"))
+            fig.add_trace(go.Scatter(x=a, y=np.sqrt(np.maximum(Dlim ** 2 - a ** 2, 0.0)), mode='lines',
+                                     name="Decision Limit"))
+            fig.update_layout(width=600, height=600, xaxis_title="T2 red", yaxis_title="Q red")
+            figs.append(fig)
+        return figs[0] if len(figs) == 1 else figs
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)

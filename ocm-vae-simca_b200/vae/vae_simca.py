@@ -1,0 +1,205 @@
+"""VAE-SIMCA decision utilities on the device.
+
+Drop-in for
+  * `VAESIMCA`       /root/reference/VAE_SIMCA.py:215-382 (fit_thresholds / predict)
+  * `compute_q_h_f`  /root/reference/vae_model.py:162-181
+  * the V1-V3 rules of the reference's VAE scripts (utils/new_vae_simca.py:397-457,
+    utils/new_vae_simca_Q.py:429-502, utils/final_vaesimca.py:500-533) as
+    `mahalanobis_rule`, `mahalanobis_and_q_rule`, `full_distance_rule`.
+
+The encoder/decoder is the torch module (vae/convvae.py); everything after it -- latent
+Mahalanobis T2, reconstruction / round-trip Q -- is one fused CUDA kernel
+(ocm_latent_score_f32) reading the activations where they already are, instead of the
+reference's per-batch `.cpu().numpy()` + einsum (VAE_SIMCA.py:359-365).  Limits are O(1)
+host arithmetic on the calibration distances.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import special
+from scipy.stats import chi2
+
+from .. import engine
+
+
+def _batches(loader, device):
+    for xb in loader:
+        x = xb[0] if isinstance(xb, (tuple, list)) else xb
+        yield x.to(device, non_blocking=True)
+
+
+def _latent_cov_inv(mu, eps):
+    """mean and pinv(cov + eps I) of calibration latents, moments by the Gram kernel in fp64."""
+    torch = engine._torch()
+    Cm, mean, _ = engine.covariance(mu.to(torch.float32).contiguous())
+    Cm = Cm + eps * torch.eye(Cm.shape[0], dtype=Cm.dtype, device=Cm.device)
+    return mean, torch.linalg.pinv(Cm)
+
+
+class VAESIMCA:
+    def __init__(self, vae, type='alt', t2lim='Fdist', t2cl=0.95, qlim='jm', qcl=0.95, dcl=0.95,
+                 device='cuda', verbose=True):
+        self.vae = vae
+        self.device = device
+        self.type = type
+        self.t2lim, self.t2cl = t2lim, t2cl
+        self.qlim, self.qcl = qlim, qcl
+        self.dcl = dcl
+        self.verbose = verbose
+        self._model = {}
+        self.model_class = None
+
+    # latent mean and its decode->encode round trip, all resident on the device
+    def _latents(self, loader):
+        torch = engine._torch()
+        mus, hats = [], []
+        with torch.no_grad():
+            for x in _batches(loader, self.device):
+                mu, _ = self.vae.encode((x - self.vae.spec_mean) / self.vae.spec_std)
+                x_hat = self.vae.decode(mu)
+                mu_hat, _ = self.vae.encode((x_hat - self.vae.spec_mean) / self.vae.spec_std)
+                mus.append(mu.float()); hats.append(mu_hat.float())
+        return torch.cat(mus), torch.cat(hats)
+
+    def fit_thresholds(self, loader, class_label=0):
+        """VAE_SIMCA.py:231-279."""
+        self.vae.eval()
+        self.model_class = [class_label]
+        mu, mu_hat = self._latents(loader)
+        d = mu.shape[1]
+        mean, Sinv = _latent_cov_inv(mu, 1e-12)
+        T2, Q = engine.latent_score(z=mu, m=mean, Sinv=Sinv, x=mu, xrec=mu_hat)
+        T2 = T2.double().cpu().numpy(); Q = Q.cpu().numpy()
+        T2_limit, t2dof, t2sc = self._compute_T2_limit(T2, d)
+        Q_limit, qdof, qsc = self._compute_Q_limit(Q)
+        D_limit = self._compute_D_limit(T2_limit, Q_limit, T2, Q, d, t2dof, t2sc, qdof, qsc)
+        self._model[class_label] = {
+            "latent_mean": mean.cpu().numpy(), "invcovT": Sinv.cpu().numpy(), "T2": T2, "Q": Q,
+            "T2_limit": T2_limit, "Q_limit": Q_limit, "D_limit": D_limit, "T2dof": t2dof,
+            "T2scfact": t2sc, "Qdof": qdof, "Qscfact": qsc, "n_components": d,
+            "_mean": mean, "_Sinv": Sinv}
+
+    def _compute_T2_limit(self, T2, n_components):
+        """VAE_SIMCA.py:281-300 (percentile-flavoured on purpose)."""
+        n = len(T2)
+        pc = np.percentile(T2, self.t2cl * 100)
+        if self.t2lim in ('perc', 'chi2'):
+            return pc, None, None
+        if self.t2lim == 'Fdist':
+            return n_components * (n - 1) / (n - n_components) * pc, None, None
+        if self.t2lim == 'chi2pom':
+            h0 = float(np.mean(T2))
+            var = float(np.var(T2, ddof=1)) if n > 1 else 0.0
+            Nh = max(int(np.round(2 * h0 ** 2 / var)) if var > 0 else 1, 1)
+            return h0 * pc / Nh, Nh, h0
+        raise ValueError(f"T2 limit type {self.t2lim} not implemented")
+
+    def _compute_Q_limit(self, Q):
+        """VAE_SIMCA.py:302-327."""
+        if self.qlim == 'perc':
+            return np.percentile(Q, self.qcl * 100), None, None
+        if self.qlim == 'jm':
+            Qd = Q
+            th1, th2, th3 = Qd.sum(), np.sum(Qd ** 2), np.sum(Qd ** 3)
+            if th1 == 0:
+                return 0, None, None
+            h0 = max(1 - (2 * th1 * th3) / (3 * th2 ** 2), 1e-3)
+            ca = np.sqrt(2) * special.erfinv(2 * self.qcl - 1)
+            h1 = ca * np.sqrt(2 * th2 * h0 ** 2) / th1
+            h2 = th2 * h0 * (h0 - 1) / th1 ** 2
+            return th1 * (1 + h1 + h2) ** (1 / h0), None, None
+        if self.qlim == 'chi2pom':
+            v0 = np.mean(Q)
+            Nv = max(round(2 * v0 ** 2 / np.var(Q, ddof=1)), 1)
+            return v0 * np.percentile(Q, self.qcl * 100) / Nv, Nv, v0
+        raise ValueError(f"Q limit type {self.qlim} not implemented")
+
+    def _compute_D_limit(self, T2_limit, Q_limit, T2, Q, n_components, t2dof=None, t2scfact=None,
+                         qdof=None, qscfact=None):
+        """VAE_SIMCA.py:329-346."""
+        if self.type == 'sim':
+            return 1
+        if self.type == 'alt':
+            return np.sqrt(2)
+        if self.type == 'ci':
+            tr1 = n_components / T2_limit + np.sum(Q) / Q_limit
+            tr2 = n_components / T2_limit ** 2 + np.sum(Q ** 2) / Q_limit ** 2
+            return (tr2 / tr1) * np.percentile(Q, self.dcl * 100)
+        if self.type == 'dd':
+            if t2dof is None or qdof is None:
+                raise ValueError("t2dof/qdoff must be set for dd")
+            return t2dof + qdof
+        raise ValueError(f"D type {self.type} not implemented")
+
+    def predict(self, loader):
+        """VAE_SIMCA.py:349-382 -> (y_pred bool[N], T2[N], Q[N]) as numpy."""
+        self.vae.eval()
+        info = self._model[self.model_class[0]]
+        mu, mu_hat = self._latents(loader)
+        T2, Q = engine.latent_score(z=mu, m=info["_mean"], Sinv=info["_Sinv"], x=mu, xrec=mu_hat)
+        T2 = T2.double().cpu().numpy(); Q = Q.cpu().numpy()
+        if self.type == 'alt':
+            D = np.sqrt((T2 / info["T2_limit"]) ** 2 + (Q / info["Q_limit"]) ** 2)
+        elif self.type == 'dd':
+            D = T2 * info["T2dof"] / info["T2scfact"] + Q * info["Qdof"] / info["Qscfact"]
+        else:
+            D = np.maximum(T2 / info["T2_limit"], Q / info["Q_limit"])
+        return D < info["D_limit"], T2, Q
+
+
+def latent_recon_scores(vae, x, sample=False, recon_dtype=None):
+    """Config-5 scoring step: one encoder pass, deterministic reconstruction dec(mu) (the reference
+    re-encodes and SAMPLES z for the reconstruction, final_vaesimca.py:478-483 -- SURVEY Q6), then
+    ONE fused kernel: d2 against (vae.latent_mean, vae.latent_cov_inv) and q = |x - x_rec|^2."""
+    torch = engine._torch()
+    with torch.no_grad():
+        x_rec, mu, _ = vae(x, sample=sample)
+        if recon_dtype is not None:
+            x_rec = x_rec.to(recon_dtype)
+        d2, q = engine.latent_score(z=mu.float(), m=vae.latent_mean, Sinv=vae.latent_cov_inv,
+                                    x=x.float(), xrec=x_rec)
+    return d2, q, mu
+
+
+def compute_q_h_f(x, x_rec, z):
+    """vae_model.py:162-181 on the device: q = |x - x_rec|^2; h = leverage of the batch-standardised
+    latent (|U_i|^2 of its thin SVD == z_i (Z^T Z)^-1 z_i^T, evaluated by the Mahalanobis kernel);
+    chi-square moment matching; f = h/h0*Nh + q/q0*Nq.  Returns (q, h, f, q_crit, h_crit, f_crit)."""
+    torch = engine._torch()
+    z = z.float()
+    zs = ((z - z.mean(dim=0)) / (z.std(dim=0) + 1e-12)).contiguous()
+    G = engine.gram(zs)                                   # upper triangle of Zs^T Zs, fp64
+    G = torch.triu(G) + torch.triu(G, 1).T
+    Ginv = torch.linalg.pinv(G)
+    zero = torch.zeros(z.shape[1], device=z.device)
+    h, q = engine.latent_score(z=zs, m=zero, Sinv=Ginv, x=x.float().contiguous(), xrec=x_rec.float().contiguous())
+    q0, sq = q.mean().item(), q.std(unbiased=True).item()
+    h0, sh = h.mean().item(), h.std(unbiased=True).item()
+    Nq, Nh = 2 * (q0 / sq) ** 2, 2 * (h0 / sh) ** 2
+    f = (h / h0) * Nh + (q / q0) * Nq
+    return q, h, f, chi2.ppf(0.95, df=Nq), chi2.ppf(0.95, df=Nh), chi2.ppf(0.95, df=Nh + Nq)
+
+
+# ---- the script-level decision rules (V1-V3), as functions over device distances -------------
+def mahalanobis_rule(d2_cal, d2_test, pct=95.0):
+    """V1: accept when latent d2 <= P95 of the calibration d2 (utils/new_vae_simca.py:397-409,:441-457)."""
+    thr = float(np.percentile(d2_cal.cpu().numpy(), pct))
+    return d2_test <= thr, thr
+
+
+def mahalanobis_and_q_rule(d2_cal, q_cal, d2_test, q_test, pct=95.0):
+    """V2: V1 and q <= P95(q_cal) (utils/new_vae_simca_Q.py:429-453,:492-502)."""
+    a, t1 = mahalanobis_rule(d2_cal, d2_test, pct)
+    t2 = float(np.percentile(q_cal.cpu().numpy(), pct))
+    return a & (q_test <= t2), (t1, t2)
+
+
+def full_distance_rule(h, q, cl=0.95):
+    """V3: f = h/h0*Nh + q/q0*Nq <= chi2(cl; Nh+Nq); h = |mu - m|^2 (latent_score with Sinv = I),
+    moments (population std) of the scored set itself (utils/final_vaesimca.py:500-533)."""
+    h0, sh = h.mean().item(), h.std(unbiased=False).item()
+    q0, sq = q.mean().item(), q.std(unbiased=False).item()
+    Nh, Nq = 2 * (h0 / sh) ** 2, 2 * (q0 / sq) ** 2
+    f = h / h0 * Nh + q / q0 * Nq
+    crit = float(chi2.ppf(cl, Nh + Nq))
+    return f <= crit, f, crit

@@ -1,0 +1,298 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the CPU
+oracle and against the committed golden fixtures of the live reference.
+
+Tolerances (BASELINE.json north_star): eigenvalues / loadings from the fp64 fit path 1e-8,
+T2 and Q within 1e-5 relative (fp32 kernels), limits 1e-6, decisions identical except for
+samples whose reduced distance lies within 1e-4 of the critical limit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ocm_vae_simca_b200 as ocm
+from ocm_vae_simca_b200 import engine, limits, native, synth
+from ocm_vae_simca_b200.utils import SIMCA, cross_validate_simca_grid
+from oracle import simca_oracle as so
+from oracle import vae_oracle as vo
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch
+
+
+def sign_norm(P):
+    idx = np.argmax(np.abs(P), axis=1)
+    return P * np.sign(P[np.arange(P.shape[0]), idx])[:, None]
+
+
+def assert_decisions(pred, ref_pred, dred, dlim, tol=1e-4):
+    diff = pred != ref_pred
+    if diff.any():
+        border = np.abs(dred[diff] / dlim - 1.0) < tol
+        assert border.all(), f"{int((~border).sum())} non-borderline decision mismatches"
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_c1_against_reference_golden(torch, golden_dir):
+    g = load(golden_dir, "c1_fit_predict.npz")
+    X, y = synth.make_class_dataset(200, 100, 700, seed=0)
+    l0 = native.launch_count()
+    m = SIMCA(n_components=5, model_class=0, verbose=False).fit(X, y)
+    info = m._model[0]
+    np.testing.assert_allclose(info["eigs_all"][:150], g["eigs_all"][:150], rtol=1e-8)
+    np.testing.assert_allclose(info["eigs_all"].sum(), g["eigs_all"].sum(), rtol=1e-10)
+    np.testing.assert_allclose(sign_norm(info["P"]), sign_norm(g["P"]), atol=1e-8)
+    np.testing.assert_allclose(info["xmean"], g["xmean"], rtol=1e-12)
+    np.testing.assert_allclose(info["T2"], g["T2_train"], rtol=RTOL)
+    np.testing.assert_allclose(info["Q"], g["Q_train"], rtol=RTOL)
+    np.testing.assert_allclose(np.abs(info["T"]), np.abs(so.fit_one_class(X[y == 0], 5)["T"]), rtol=1e-4, atol=1e-6)
+    for k in ("T2_limit", "Q_limit", "D_limit"):
+        np.testing.assert_allclose(info[k], g[k], rtol=1e-6)
+    assert info["eigs_all"].shape == g["eigs_all"].shape and info["invcovT"].shape == (5, 5)
+    pred = m.predict(X)
+    T2, T2red, Q, Qred = m.transform(X)
+    assert pred.shape == (300, 1) and pred.dtype == np.float64
+    np.testing.assert_allclose(T2, g["T2"], rtol=RTOL)
+    np.testing.assert_allclose(Q, g["Q"], rtol=RTOL)
+    np.testing.assert_allclose(T2red, g["T2red"], rtol=RTOL)
+    np.testing.assert_allclose(Qred, g["Qred"], rtol=RTOL)
+    dred = np.sqrt(g["T2red"] ** 2 + g["Qred"] ** 2)
+    assert_decisions(pred[:, 0], g["pred"][:, 0], dred, g["D_limit"])
+    assert native.launch_count() > l0
+
+
+def test_all_rules_and_limits(torch, golden_dir):
+    g = load(golden_dir, "limits_grid.npz")
+    X, y = synth.make_class_dataset(120, 40, 90, seed=11)
+    for i, name in enumerate(g["names"]):
+        kind, t2l, ql = str(name).split("/")
+        m = SIMCA(n_components=4, model_class=0, type=kind, t2lim=t2l, qlim=ql, verbose=False)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.fit(X, y)
+            pred = m.predict(X)[:, 0]
+        info = m._model[0]
+        np.testing.assert_allclose([info["T2_limit"], info["Q_limit"], info["D_limit"]], g["limits"][i],
+                                   rtol=2e-5, err_msg=str(name))
+        ref = so.fit_one_class(X[y == 0], 4, kind=kind, t2lim=t2l, qlim=ql)
+        T2r, Qr = so.score(ref, X)
+        assert_decisions(pred, g["preds"][i].astype(float), so.reduced_distance(ref, T2r, Qr), ref["D_limit"], tol=2e-4)
+
+
+def test_float32_and_device_tensor_inputs(torch):
+    X, y = synth.make_class_dataset(150, 50, 256, seed=3)
+    ref = so.fit_one_class(X[y == 0], 6)
+    T2r, Qr = so.score(ref, X)
+    m = SIMCA(n_components=6, model_class=0, verbose=False).fit(X.astype(np.float32), y)
+    Xd = torch.as_tensor(X.astype(np.float32), device="cuda")
+    T2, _, Q, _ = m.transform(Xd)
+    assert T2.is_cuda
+    np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=3e-5)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=3e-5)
+    pred = m.predict(Xd)
+    assert pred.is_cuda and pred.shape == (200, 1)
+
+
+def test_ncomp_sweep_multiA(torch, golden_dir):
+    g = load(golden_dir, "ncomp_sweep.npz")
+    X, y = synth.make_class_dataset(300, 100, 300, seed=21)
+    Xte, _ = synth.make_class_dataset(60, 60, 300, seed=22)
+    Xd = engine.to_device(X)
+    idx = engine.index_tensor(np.flatnonzero(y == 0), Xd.device)
+    pca = engine.fit_pca(Xd, idx, 20)
+    inv = torch.as_tensor(1.0 / pca.eigs_all[:20], device=Xd.device)
+    T2, Q, _ = engine.score_multiA(engine.to_device(Xte), pca.mean, pca.P, inv)
+    T2, Q = T2.cpu().numpy(), Q.cpu().numpy()
+    for i, A in enumerate(g["A_values"]):
+        np.testing.assert_allclose(T2[:, A - 1], g["T2"][i], rtol=RTOL, err_msg=f"A={A}")
+        np.testing.assert_allclose(Q[:, A - 1], g["Q"][i], rtol=RTOL, err_msg=f"A={A}")
+        lim = limits.all_limits("alt", "Fdist", 0.95, "jm", 0.95, 0.95, int(A), 300, pca.eigs_all)
+        np.testing.assert_allclose([lim.T2_limit, lim.Q_limit, lim.D_limit], g["limits"][i], rtol=1e-6)
+    # single-model kernel agrees with the multi-A kernel column
+    for A in (1, 7, 20):
+        Sinv = torch.diag(inv[:A])
+        t2s, qs, _ = engine.score(engine.to_device(Xte), pca.mean, pca.P[:A], Sinv)
+        np.testing.assert_allclose(t2s.cpu().numpy(), T2[:, A - 1], rtol=2e-6)
+        np.testing.assert_allclose(qs.cpu().numpy(), Q[:, A - 1], rtol=2e-5)
+
+
+def test_ncomp_one_works(torch):
+    X, y = synth.make_class_dataset(80, 20, 40, seed=5)
+    m = SIMCA(n_components=1, model_class=0, verbose=False).fit(X, y)
+    ref = so.fit_one_class(X[y == 0], 1)
+    T2r, Qr = so.score(ref, X)
+    T2, _, Q, _ = m.transform(X)
+    np.testing.assert_allclose(T2, T2r, rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(Q, Qr, rtol=RTOL)
+
+
+def test_cv_small_table(torch, golden_dir):
+    from sklearn.model_selection import PredefinedSplit
+    g = load(golden_dir, "cv_small.npz")
+    X, y = synth.make_class_dataset(270, 90, 150, seed=31)
+    cv = PredefinedSplit(np.arange(X.shape[0]) % 6)
+    for batched in (True, False):
+        res = cross_validate_simca_grid(SIMCA(model_class=0, verbose=False), X, y, cv, LV_min=2, LV_max=8,
+                                        class_index=0, print_summary=False, store_predictions=True, batched=batched)
+        table = np.array([[r["LV"], r["spec"], r["sens"], r["eff"]] for r in res["results"]])
+        pooled = np.array([b["prediction"] for b in res["by_combo"]]).astype(np.uint8)
+        flips = int((pooled != g["pooled"]).sum())
+        assert flips <= 2, f"{flips} pooled decisions differ from the reference (batched={batched})"
+        if flips == 0:
+            np.testing.assert_allclose(table, g["table"], rtol=1e-12)
+            assert res["best_LV"] == int(g["best_LV"])
+        assert res["best_estimator"].is_fitted_
+
+
+def test_cv_param_grid_and_lv1(torch):
+    from sklearn.model_selection import PredefinedSplit
+    X, y = synth.make_class_dataset(200, 80, 120, seed=41)
+    cv = PredefinedSplit(np.arange(X.shape[0]) % 5)
+    grid = {"type": ["alt", "sim"], "qlim": ["jm", "chi2box"]}
+    res_b = cross_validate_simca_grid(SIMCA(model_class=0, verbose=False), X, y, cv, LV_min=1, LV_max=6,
+                                      param_grid=grid, class_index=0, print_summary=False, batched=True)
+    assert len(res_b["results"]) == 4 * 6
+    splits = list(cv.split())
+    for r in res_b["results"][::5]:
+        o = so.cv_grid(X, y, splits, [r["LV"]], model_class=0, refit=False, kind=r["params"]["type"],
+                       qlim=r["params"]["qlim"])["results"][0]
+        assert abs(o["sens"] - r["sens"]) < 1.0 and abs(o["spec"] - r["spec"]) < 2.0
+
+
+def test_preprocess_kernels(torch):
+    rng = np.random.default_rng(0)
+    for p in (700, 1024, 1050):
+        X = (rng.normal(1.0, 0.3, (257, p))).astype(np.float32)
+        out = engine.snv(X).cpu().numpy()
+        np.testing.assert_allclose(out, so.snv(X.astype(np.float64)), rtol=2e-5, atol=2e-5)
+        mu = X.mean(0); sd = X.std(0) + 1e-8
+        np.testing.assert_allclose(engine.preprocess(X, "center", mu=mu).cpu().numpy(), X - mu, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(engine.preprocess(X, "autoscale", mu=mu, sigma=sd).cpu().numpy(), (X - mu) / sd,
+                                   rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(engine.preprocess(X, "snv_center", mu=mu).cpu().numpy(),
+                                   so.snv(X.astype(np.float64)) - mu, rtol=2e-5, atol=2e-5)
+    assert engine.snv(np.zeros((0, 16), np.float32)).shape == (0, 16)
+
+
+def test_fused_snv_scoring(torch):
+    Xraw = synth.make_spectra(300, 512, seed=8)
+    Xs = so.snv(Xraw)
+    ref = so.fit_one_class(Xs[:200], 5)
+    T2r, Qr = so.score(ref, Xs)
+    dev = torch.device("cuda")
+    T2, Q, _ = engine.score(torch.as_tensor(Xraw.astype(np.float32), device=dev),
+                            torch.as_tensor(ref["pred_mean"], device=dev), torch.as_tensor(ref["pred_P"], device=dev),
+                            torch.as_tensor(ref["Sinv"], device=dev), snv=True)
+    np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=2e-4)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=2e-4)
+
+
+def test_scoring_properties_at_bulk_shape(torch):
+    """Size-independent properties at p=1024, A=10 on 300k device-generated rows."""
+    dev = torch.device("cuda")
+    n, p, A = 300_000, 1024, 10
+    X = synth.make_spectra_device(n, p, dev, seed=5)
+    pca = engine.fit_pca(X[:5000].contiguous(), None, A)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+    T2, Q, acc = engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=1 / 20.0, cq=1 / 0.01, dlim=np.sqrt(2))
+    # (1) chunked == whole, bit for bit
+    T2b, Qb, accb = engine.score(X[100_003:200_001], pca.mean, pca.P, Sinv, rule="alt", ct=1 / 20.0, cq=1 / 0.01,
+                                 dlim=np.sqrt(2))
+    assert torch.equal(T2[100_003:200_001], T2b) and torch.equal(Q[100_003:200_001], Qb)
+    assert torch.equal(acc[100_003:200_001], accb)
+    # (2) a row inside the model plane has Q ~ 0 and T2 = sum t^2/lambda
+    t = torch.randn(64, A, device=dev, dtype=torch.float64) * torch.as_tensor(np.sqrt(pca.eigs_all[:A]), device=dev)
+    Xin = (pca.mean + t @ pca.P).float()
+    T2i, Qi, _ = engine.score(Xin, pca.mean, pca.P, Sinv)
+    np.testing.assert_allclose(T2i.cpu().numpy(), ((t ** 2).cpu().numpy() / pca.eigs_all[:A]).sum(1), rtol=1e-4)
+    assert float(Qi.max()) < 1e-9 * float((Xin - pca.mean.float()).pow(2).sum(1).max())
+    # (3) subset check against the oracle arithmetic in fp64
+    sub = X[::30_011].double().cpu().numpy()
+    model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+    T2r, Qr = so.score(model, sub)
+    np.testing.assert_allclose(T2[::30_011].cpu().numpy(), T2r, rtol=RTOL)
+    np.testing.assert_allclose(Q[::30_011].cpu().numpy(), Qr, rtol=RTOL)
+    # (4) decisions consistent with the distances the kernel wrote
+    d = torch.sqrt((T2 / 20.0) ** 2 + (Q / 0.01) ** 2)
+    clear = (d / np.sqrt(2) - 1).abs() > 1e-5
+    assert torch.equal((d < np.sqrt(2))[clear], acc.bool()[clear])
+
+
+def test_host_buffer_api(torch):
+    X = synth.make_spectra(5000, 1024, seed=12).astype(np.float32)
+    ref = so.fit_one_class(X[:2000].astype(np.float64), 10)
+    T2r, Qr = so.score(ref, X.astype(np.float64))
+    mu = ref["pred_mean"].astype(np.float32); P = np.ascontiguousarray(ref["pred_P"], np.float32)
+    S = np.ascontiguousarray(ref["Sinv"], np.float32)
+    T2 = np.empty(5000, np.float32); Q = np.empty(5000, np.float32); acc = np.empty(5000, np.uint8)
+    prm = native.ScoreParams(A=10, rule=1, snv=0, snv_eps=1e-8, ct=1.0 / ref["T2_limit"], cq=1.0 / ref["Q_limit"],
+                             dlim=float(ref["D_limit"]))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = native.lib().ocm_simca_score_host_f32(vp(X), 5000, 1024, 1024, vp(mu), vp(P), vp(S), C.byref(prm), 1536,
+                                               vp(T2), vp(Q), vp(acc))
+    native.check(rc)
+    np.testing.assert_allclose(T2, T2r, rtol=3e-5)
+    np.testing.assert_allclose(Q, Qr, rtol=3e-5)
+    assert_decisions(acc.astype(float), so.predict(ref, X.astype(np.float64)), so.reduced_distance(ref, T2r, Qr),
+                     ref["D_limit"])
+
+
+def test_bad_arguments_raise(torch):
+    prm = native.ScoreParams(A=65, rule=1)
+    rc = native.lib().ocm_simca_score_f32(None, 1, 8, 8, None, None, None, C.byref(prm), None, None, None, None, None)
+    assert rc < 0 and b"NULL" in native.lib().ocm_last_error()
+    X, y = synth.make_class_dataset(40, 10, 30, seed=1)
+    with pytest.raises(ValueError):
+        SIMCA(n_components=[2, 3], model_class=0).fit(X, y)
+
+
+def test_latent_score_and_vae_simca(torch, golden_dir):
+    from ocm_vae_simca_b200.vae import ConvVAE1D, VAESIMCA, compute_q_h_f
+    g = load(golden_dir, "vae_qhf.npz")
+    dev = torch.device("cuda")
+    q, h, f, qc, hc, fc = compute_q_h_f(torch.as_tensor(g["x"], device=dev), torch.as_tensor(g["x_rec"], device=dev),
+                                        torch.as_tensor(g["z"], device=dev))
+    np.testing.assert_allclose(q.cpu().numpy(), g["q"], rtol=2e-5)
+    np.testing.assert_allclose(h.cpu().numpy(), g["h"], rtol=5e-4)
+    np.testing.assert_allclose(f.cpu().numpy(), g["f"], rtol=1e-3)
+    np.testing.assert_allclose([qc, hc, fc], g["crit"], rtol=1e-3)
+    # bf16 reconstruction input
+    x = torch.as_tensor(g["x"], device=dev); xr = torch.as_tensor(g["x_rec"], device=dev).to(torch.bfloat16)
+    _, qb = engine.latent_score(x=x, xrec=xr)
+    np.testing.assert_allclose(qb.cpu().numpy(), ((g["x"] - xr.float().cpu().numpy()) ** 2).sum(1), rtol=2e-5)
+
+    gv = load(golden_dir, "vae_simca.npz")
+    L, d = int(gv["L"]), int(gv["d"])
+    vae = ConvVAE1D(L, d, np.zeros(L, np.float32), np.ones(L, np.float32), conv_blocks=2, n_filters=4,
+                    kernel_size=5, hidden_fc=16)
+    vae.load_state_dict({str(k): torch.from_numpy(gv["sd::" + str(k)]) for k in gv["state_keys"]})
+    vae = vae.to(dev).eval()
+    Xcal, Xte = torch.from_numpy(gv["Xcal"]), torch.from_numpy(gv["Xte"])
+    for tag in ("alt_Fdist_jm", "sim_perc_perc", "dd_chi2pom_chi2pom", "alt_chi2_jm"):
+        kind, t2l, ql = tag.split("_")
+        vs = VAESIMCA(vae, type=kind, t2lim=t2l, qlim=ql, device=dev, verbose=False)
+        vs.fit_thresholds([(Xcal,)], class_label=0)
+        yp, T2, Q = vs.predict([(Xte,)])
+        mi = vs._model[0]
+        np.testing.assert_allclose([mi["T2_limit"], mi["Q_limit"], mi["D_limit"]], gv[tag + "::limits"], rtol=2e-3)
+        np.testing.assert_allclose(T2, gv[tag + "::T2"], rtol=2e-3)
+        np.testing.assert_allclose(Q, gv[tag + "::Q"], rtol=2e-3, atol=1e-6)
+        assert np.mean(yp.astype(np.uint8) != gv[tag + "::pred"]) < 0.03
+
+
+def test_smoke_entry(torch):
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,145 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, host-side logic
+(estimator protocol, splitter, limits, row sharding, gloo all-reduce of moments)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ocm_vae_simca_b200 as ocm
+from ocm_vae_simca_b200 import dist as odist
+from ocm_vae_simca_b200 import limits, native, synth
+from ocm_vae_simca_b200.utils import SIMCA, ClasswiseKFoldWithExternalVal, cross_validate_simca_grid
+from ocm_vae_simca_b200.utils.CVSIMCA import _find_ncomp_param_name, _get_simca
+from oracle import simca_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ocm_simca.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocm_[a-z0-9_A-Z]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    native.build()
+    import ctypes
+    handle = ctypes.CDLL(native.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/ocm_simca.h but not exported"
+    assert native.lib().ocm_abi_version() == 1
+    # every bound signature is declared in the header as well
+    for s in native.SIGNATURES:
+        assert s in syms, f"{s} bound in native.py but not declared in the header"
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    X, y = synth.make_class_dataset(40, 10, 30, seed=1)
+    with pytest.raises(native.NativeError):
+        SIMCA(n_components=2, model_class=0).fit(X, y)
+
+
+def test_estimator_protocol():
+    from sklearn.base import clone
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    m = SIMCA(n_components=3, model_class=0, type="ci", qlim="chi2box")
+    c = clone(m)
+    assert c.get_params()["type"] == "ci" and c.get_params()["n_components"] == 3
+    c.set_params(n_components=7)
+    assert c.n_components == 7
+    pipe = Pipeline([("sc", StandardScaler()), ("simca", SIMCA(model_class=0))])
+    assert _get_simca(pipe) is pipe.named_steps["simca"]
+    assert _find_ncomp_param_name(pipe) == "simca__n_components"
+    assert _find_ncomp_param_name(m) == "n_components"
+    with pytest.raises(AttributeError):
+        _get_simca(StandardScaler())
+
+
+def test_metrics_match_oracle():
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 2, 200); p = rng.integers(0, 2, 200).astype(float)
+    a = SIMCA()._metrics_simca_conformity(y, p, 0)
+    b = so.conformity(y, p, 0)
+    for k in ("TP", "TN", "FP", "FN"):
+        assert int(a[k]) == int(b[k])
+    for k in ("sensitivity", "specificity", "accuracy", "efficiency"):
+        np.testing.assert_allclose(a[k], b[k])
+
+
+def test_classwise_kfold_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "classwise_kfold.npz"))
+    X, y = synth.make_class_dataset(270, 90, 150, seed=31)
+    sp = ClasswiseKFoldWithExternalVal(n_splits=4, cls_label=0)
+    for i, (tr, te) in enumerate(sp.split(X, y)):
+        assert np.array_equal(tr, g[f"tr{i}"]) and np.array_equal(te, g[f"te{i}"])
+    with pytest.raises(ValueError):
+        list(ClasswiseKFoldWithExternalVal(n_splits=4, cls_label=0).split(X))
+    with pytest.raises(ValueError):
+        list(ClasswiseKFoldWithExternalVal(n_splits=4, cls_label=7).split(X, y))
+
+
+def test_limits_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "limits_grid.npz"))
+    X, y = synth.make_class_dataset(120, 40, 90, seed=11)
+    base = so.fit_one_class(X[y == 0], 4)
+    for i, name in enumerate(g["names"]):
+        kind, t2l, ql = str(name).split("/")
+        if kind == "dd":
+            t2l = ql = "chi2pom"
+        lim = limits.all_limits(kind, t2l, 0.95, ql, 0.95, 0.95, 4, base["n_samples"], base["eigs_all"],
+                                base["T2"], base["Q"])
+        np.testing.assert_allclose([lim.T2_limit, lim.Q_limit, lim.D_limit], g["limits"][i], rtol=1e-9,
+                                   err_msg=str(name))
+
+
+def test_shard_rows_partition():
+    for n, w in [(10, 3), (7, 8), (10_000_000, 8), (0, 2)]:
+        spans = [odist.shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    odist.init("gloo")
+    X = synth.make_spectra(301, 40, seed=3)
+    lo, hi = odist.shard_rows(X.shape[0], rank, world)
+    shift = X[:50].mean(0)
+    Xs = X[lo:hi] - shift
+    G = torch.from_numpy(Xs.T @ Xs)
+    s = torch.from_numpy(Xs.sum(0))
+    n = odist.allreduce_moments(G, s, hi - lo)
+    d = s.numpy() / n
+    C = (G.numpy() - n * np.outer(d, d)) / (n - 1)
+    tabs = odist.allgather_counts(torch.tensor([[rank, 1, 2, 3]], dtype=torch.int64))
+    mx = odist.max_over_ranks(float(rank), "cpu")
+    if rank == 0:
+        q.put((n, float(np.abs(C - np.cov(X, rowvar=False)).max()), [int(t[0, 0]) for t in tabs], mx))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_moment_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n, err, ranks, mx = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert n == 301 and err < 1e-12 and ranks == [0, 1] and mx == 1.0
