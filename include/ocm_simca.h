@@ -119,6 +119,14 @@ int ocm_simca_score_simt_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
                              const ocm_score_params* h_params,
                              float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
 
+/* the register-resident "row team" FP32-pipe kernel (bulk shapes: p in {512,1024,2048}, even
+ * n_components <= 12, 16-byte aligned rows, no fused SNV) and its shape gate */
+int ocm_simca_score_rowteam_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+int ocm_simca_score_rowteam_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                                const float* mu, const float* P, const float* Sinv,
+                                const ocm_score_params* h_params,
+                                float* T2, float* Q, uint8_t* accept, void* stream);
+
 /* 1 when ocm_simca_score_f32 would take the tcgen05/TMA kernel for this shape (bulk path:
  * fp32, p a multiple of the K-slice, 16-byte aligned rows), else 0. */
 int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);

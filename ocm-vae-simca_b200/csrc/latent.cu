@@ -83,7 +83,8 @@ extern "C" int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_
                                     int32_t xrec_is_bf16, int32_t p, int64_t ldx, int64_t ldxrec,
                                     float* d2, float* q, void* stream) {
     using namespace ocm;
-    OCM_REQUIRE(n >= 0, OCM_EINVAL, "bad n");
+    if (n == 0) return 0;
+    OCM_REQUIRE(n > 0, OCM_EINVAL, "bad n");
     OCM_REQUIRE(z || x, OCM_EINVAL, "nothing to score");
     if (z) {
         OCM_REQUIRE(m && Sinv && d2 && d >= 1 && ldz >= d, OCM_EINVAL, "latent part needs m, Sinv, d2");

@@ -148,8 +148,8 @@ cov_from_parts_kernel(const double* __restrict__ Gparts, PartsArgs a, int p,
 template <typename T>
 int colstats_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                   const double* shift, double* colsum, double* colsumsq, void* stream) {
-    OCM_REQUIRE(X && colsum && n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
     if (n == 0) return 0;
+    OCM_REQUIRE(X && colsum && n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
     int64_t rb = (n + 63) / 64;
     int64_t cap = (int64_t)sm_count() * 8 / ((p + 255) / 256) + 1;
     if (rb > cap) rb = cap;
@@ -162,8 +162,8 @@ int colstats_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, in
 template <typename T>
 int gram_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
               const double* shift, double* G, void* stream) {
-    OCM_REQUIRE(X && G && n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
     if (n == 0) return 0;
+    OCM_REQUIRE(X && G && n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
     const int nt = (p + GT - 1) / GT;
     const int ntiles = nt * (nt + 1) / 2;
     // enough K-splits to fill the machine ~2 waves, at least 64 rows per split

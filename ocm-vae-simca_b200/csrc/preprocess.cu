@@ -119,7 +119,8 @@ extern "C" int ocm_preprocess_f32(const float* X, int64_t n, int32_t p, int64_t 
                                   const float* mu, const float* sigma, float eps,
                                   float* Y, int64_t ldy, void* stream) {
     using namespace ocm;
-    OCM_REQUIRE(X && Y && n >= 0 && p > 0 && ldx >= p && ldy >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    if (n == 0) return 0;   // empty input: nothing to do (pointers of empty buffers may be NULL)
+    OCM_REQUIRE(X && Y && n > 0 && p > 0 && ldx >= p && ldy >= p, OCM_EINVAL, "bad shape or NULL buffer");
     OCM_REQUIRE(mode >= OCM_PRE_SNV && mode <= OCM_PRE_SNV_CENTER, OCM_EINVAL, "unknown mode");
     OCM_REQUIRE(mode == OCM_PRE_SNV || mu, OCM_EINVAL, "mode needs mu");
     OCM_REQUIRE(mode != OCM_PRE_AUTOSCALE || sigma, OCM_EINVAL, "autoscale needs sigma");

@@ -6,13 +6,20 @@ extern "C" int ocm_simca_score_simt_f32(const float*, int64_t, int32_t, int64_t,
 extern "C" int ocm_simca_score_tc_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
                                       const float*, const ocm_score_params*, float*, float*, uint8_t*, void*);
 extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+extern "C" int ocm_simca_score_rowteam_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+extern "C" int ocm_simca_score_rowteam_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
+                                           const float*, const ocm_score_params*, float*, float*, uint8_t*, void*);
 
 extern "C" int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t ldx, const float* mu,
                                    const float* P, const float* Sinv, const ocm_score_params* hp,
                                    float* T2, float* Q, uint8_t* accept, float* scores, void* stream) {
+    if (n == 0) return 0;
     OCM_REQUIRE(hp, OCM_EINVAL, "NULL params");
     if (!scores && ocm_simca_score_tc_supported(n, p, ldx, hp->A, hp->snv, X))
         return ocm_simca_score_tc_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, stream);
+    if (!scores && ocm_simca_score_rowteam_supported(n, p, ldx, hp->A, hp->snv, X) &&
+        (reinterpret_cast<uintptr_t>(mu) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0)
+        return ocm_simca_score_rowteam_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, stream);
     return ocm_simca_score_simt_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
 }
 

@@ -247,8 +247,9 @@ template <typename TIn>
 int score_single(const TIn* X, int64_t n, int32_t p, int64_t ldx, const TIn* mu, const float* P,
                  const float* Sinv, const ocm_score_params* hp, float* T2, float* Q, uint8_t* accept,
                  float* scores, void* stream) {
+    if (n == 0) return 0;
     OCM_REQUIRE(X && mu && P && Sinv && hp, OCM_EINVAL, "NULL buffer");
-    OCM_REQUIRE(n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
+    OCM_REQUIRE(n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
     OCM_REQUIRE(hp->A >= 1 && hp->A <= 64, OCM_ELIMIT, "n_components must be 1..64");
     OCM_REQUIRE(hp->rule >= OCM_RULE_SIM && hp->rule <= OCM_RULE_DD, OCM_EINVAL, "unknown rule");
     if (n == 0) return 0;
@@ -263,8 +264,9 @@ int score_multi(const TIn* X, int64_t n, int32_t p, int64_t ldx, const TIn* mu, 
                 const float* inv_eig, int32_t Amax, int32_t rule, int32_t snv, float snv_eps,
                 const float* ct, const float* cq, const float* dlim, float* T2, float* Q,
                 uint8_t* accept, void* stream) {
+    if (n == 0) return 0;
     OCM_REQUIRE(X && mu && P && inv_eig, OCM_EINVAL, "NULL buffer");
-    OCM_REQUIRE(n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
+    OCM_REQUIRE(n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
     OCM_REQUIRE(Amax >= 1 && Amax <= 64, OCM_ELIMIT, "Amax must be 1..64");
     OCM_REQUIRE(rule >= OCM_RULE_SIM && rule <= OCM_RULE_DD, OCM_EINVAL, "unknown rule");
     OCM_REQUIRE(!accept || (ct && cq && dlim), OCM_EINVAL, "accept needs ct/cq/dlim");
@@ -322,7 +324,8 @@ extern "C" int ocm_simca_score_multiA_f64in(const double* X, int64_t n, int32_t 
 extern "C" int ocm_conformity_counts(const uint8_t* accept, const uint8_t* is_target, int64_t n, int32_t m,
                                      int64_t* counts, void* stream) {
     using namespace ocm;
-    OCM_REQUIRE(accept && is_target && counts && n >= 0 && m >= 1, OCM_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    OCM_REQUIRE(accept && is_target && counts && n > 0 && m >= 1, OCM_EINVAL, "bad arguments");
     OCM_REQUIRE(m <= 65535, OCM_ELIMIT, "too many decision columns");
     if (n == 0) return 0;
     int64_t bx = (n + 255) / 256;

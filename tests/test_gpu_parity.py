@@ -231,6 +231,43 @@ def test_scoring_properties_at_bulk_shape(torch):
     assert torch.equal((d < np.sqrt(2))[clear], acc.bool()[clear])
 
 
+def test_rowteam_kernel_matches_generic_and_oracle(torch):
+    """The register-resident bulk kernel against the generic kernel and the fp64 oracle for every
+    supported (p, A), ragged row counts included (n not a multiple of the 4-row group)."""
+    dev = torch.device("cuda")
+    for p in (512, 1024, 2048):
+        X = synth.make_spectra_device(4099, p, dev, seed=p)
+        for A in (2, 6, 10, 12):
+            pca = engine.fit_pca(X[:1500].contiguous(), None, A)
+            Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev)) + 1e-3   # exercise the full matrix
+            mu32, P32 = pca.arrays32()
+            prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
+            assert native.lib().ocm_simca_score_rowteam_supported(4099, p, p, A, 0, C.c_void_p(X.data_ptr())) == 1
+            outs = []
+            for fn in (native.lib().ocm_simca_score_rowteam_f32, None):
+                T2 = torch.empty(4099, device=dev); Q = torch.empty(4099, device=dev)
+                acc = torch.empty(4099, dtype=torch.uint8, device=dev)
+                S32 = Sinv.float().contiguous()
+                vp = lambda t: C.c_void_p(t.data_ptr())
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                if fn is not None:
+                    native.check(fn(vp(X), 4099, p, p, vp(mu32), vp(P32), vp(S32), C.byref(prm), vp(T2), vp(Q), vp(acc), st))
+                else:
+                    native.check(native.lib().ocm_simca_score_simt_f32(vp(X), 4099, p, p, vp(mu32), vp(P32), vp(S32),
+                                                                       C.byref(prm), vp(T2), vp(Q), vp(acc), None, st))
+                outs.append((T2.cpu().numpy(), Q.cpu().numpy(), acc.cpu().numpy()))
+            model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+            T2r, Qr = so.score(model, X.double().cpu().numpy())
+            for T2, Q, _ in outs:
+                np.testing.assert_allclose(T2, T2r, rtol=RTOL, err_msg=f"p={p} A={A}")
+                np.testing.assert_allclose(Q, Qr, rtol=RTOL, err_msg=f"p={p} A={A}")
+            d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
+            assert_decisions(outs[0][2].astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
+    # not supported -> the public entry point falls back to the generic kernel (odd A, p = 700)
+    assert native.lib().ocm_simca_score_rowteam_supported(10, 1024, 1024, 5, 0, C.c_void_p(X.data_ptr())) == 0
+    assert native.lib().ocm_simca_score_rowteam_supported(10, 700, 700, 4, 0, C.c_void_p(X.data_ptr())) == 0
+
+
 def test_host_buffer_api(torch):
     X = synth.make_spectra(5000, 1024, seed=12).astype(np.float32)
     ref = so.fit_one_class(X[:2000].astype(np.float64), 10)
