@@ -242,6 +242,16 @@ def main():
     synth.make_spectra_device(rows, p, device, seed=1000 + rank, out=X)
     torch.cuda.synchronize()
 
+    lib = native.lib()
+    if args.force_simt:
+        kernel_name = "score_simt_kernel"
+    elif lib.ocm_simca_score_tc_supported(rows, p, p, A, 0, C_void(X)):
+        kernel_name = "score_tc_kernel (tcgen05)"
+    elif lib.ocm_simca_score_rowteam_supported(rows, p, p, A, 0, C_void(X)):
+        kernel_name = f"score_rowteam_kernel<{A},{p // 128 if p <= 1024 else 8},{128 if p <= 1024 else 256}> (FFMA2)"
+    else:
+        kernel_name = "score_simt_kernel"
+
     def step():
         return engine.score(X, mean32, P32, Sinv, rule="alt", ct=ct, cq=cq, dlim=lim.D_limit,
                             force_simt=args.force_simt)
@@ -328,7 +338,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SPECTRUM(p) * rows,
-                     "kernel": "score_tc" if not args.force_simt and bool(native.lib().ocm_simca_score_tc_supported(rows, p, p, A, 0, C_void(X))) else "score_simt_kernel",
+                     "kernel": kernel_name,
                      "kernel_ms": kernel_ms},
         "clocks": clocks, "gpu_launches": int(launches),
         "check": {"accepted_frac": accepted / rows},
