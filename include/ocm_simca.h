@@ -130,6 +130,16 @@ int ocm_simca_score_rowteam_f32(const float* X, int64_t n, int32_t p, int64_t ld
 /* 1 when ocm_simca_score_f32 would take the tcgen05/TMA kernel for this shape (bulk path:
  * fp32, p a multiple of the K-slice, 16-byte aligned rows), else 0. */
 int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+/* the tcgen05 kernel itself (p == 1024, n_components <= 16, 16-byte aligned rows) */
+int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                           const float* mu, const float* P, const float* Sinv,
+                           const ocm_score_params* h_params,
+                           float* T2, float* Q, uint8_t* accept, void* stream);
+/* debugging aid: synchronises the device and returns 0 if no bounded mbarrier wait of the tcgen05
+ * kernel ever timed out in this process, 1 if one did, -1 on a CUDA error */
+int ocm_simca_score_tc_status(void);
+/* bring-up aid: device buffer [128][1024] that receives the residual of tile 0 (NULL switches it off) */
+int ocm_simca_score_tc_debug(float* buf);
 
 /* ---- a12: all nested models A = 1..Amax in one pass (CV grid, CVSIMCA.py:157-200) ------
  * inv_eig[Amax] = 1/lambda_a (diagonal Sinv of a PCA model).  Outputs are [n][Amax]:
