@@ -2,27 +2,38 @@
 // config 3 (fp32 rows, p = 1024, A <= 16).
 //
 // Why tensor cores for an HBM-bound op: per spectrum 2*p*A FMAs ride on 4*p bytes, so the FP32 pipe
-// and HBM balance at A = 10; the register-file read bandwidth caps the FP32-pipe kernel
-// (score_rowteam.cu) near 45 % of the FMA peak, i.e. ~43 % of the HBM roofline (ncu, profiles/).
-// tcgen05 takes its operands from TMEM / shared memory, not from the register file, and leaves the
-// CUDA cores ~6 instructions per element (centre, split, square).
+// and HBM balance at A = 10; FP32 operand delivery caps the FP32-pipe kernel (score_rowteam.cu) near
+// 45 % of the FMA peak, i.e. ~43 % of the HBM roofline (ncu, profiles/).  tcgen05 takes its operands from
+// TMEM / shared memory, not from the register file, and leaves the CUDA cores ~8 instructions per element
+// (centre, split, pack, square).
 //
 // Precision: T2 is first-order and Q second-order sensitive to the scores t, and the
-// reconstruction must be good to ~2^-22 of |x|, so both products run as 3-pass split TF32
-// (hi*hi + lo*hi + hi*lo, hi = top 19 bits, lo = exact remainder) with fp32 accumulation in TMEM,
-// and the residual is formed EXPLICITLY: the accumulator of the second product is pre-loaded with
-// the fp32 centred spectrum and the MMA subtracts T*P from it (a_negate), so D = xc - P^T t.
+// reconstruction must be good to ~2^-22 of |x|.  Every fp32 operand is therefore split EXACTLY into three
+// bf16 terms (x = b1 + b2 + b3 up to 2^-24, truncation splits, remainders exact in fp32) and each product
+// is the six MMAs (1,1) (1,2) (2,1) (2,2) (1,3) (3,1) with fp32 accumulation in TMEM.  bf16 rather than
+// split TF32 because the loadings must be BOTH a K-major operand (projection, K = wavelengths) and an
+// MN-major operand (reconstruction, K = components): for 16-bit types the K-major and MN-major 128B-swizzle
+// atoms are byte-identical, so ONE shared-memory copy of P (96 KB) serves both; kind::tf32 accepts MN-major
+// only in the 32B-base swizzle, which needs a second 128 KB copy that does not fit (found on the B200:
+// a plain MN-major tf32 descriptor is a silent no-op, tools/tc_diag.py).
+// The tensor core accumulates with truncation, so the large (1,1) products rotate over four accumulators
+// (16 chained accumulations each, bias < 1e-6).  A tcgen05.mma that accumulates into the SAME TMEM tile as its
+// predecessor waits for it (~100 cycles measured for these small N = 16 MMAs, which made the MMA warp the
+// bottleneck), so the five cross products get two accumulators each as well: 14 accumulators, and no two
+// consecutive MMAs of the projection touch the same one; the converter thread adds them with round-to-nearest.
+// The residual is formed EXPLICITLY by the tensor core: the accumulator of the second product is
+// pre-loaded with the fp32 centred spectrum and the MMAs subtract T*P from it (a_negate): D = xc - P^T t.
 //
 // Data flow of one CTA (persistent, one per SM), tile = 128 spectra x 1024 wavelengths:
-//   pass 1  32 stages of 128 x 32 floats stream HBM -> smem (cp.async ring, L2 evict_last);
-//           each of 256 converter threads owns one TMEM lane (= spectrum) and 16 columns of the stage:
-//           LDS -> centre -> split -> tcgen05.st into the A-operand buffers (hi, lo); the MMA warp issues
-//           T[128x16] += A[128x8] * P[16x8]^T (12 tcgen05.mma per stage, A from TMEM, P from smem).
+//   pass 1  16 stages of 128 x 64 floats stream HBM -> smem (cp.async ring, L2 evict_last);
+//           each of 256 converter threads owns one TMEM lane (= spectrum) and 32 columns of the stage:
+//           LDS -> centre -> 3-way split -> pack -> tcgen05.st into the A-operand buffer; the MMA warp issues
+//           T[128x16] += A[128x16] * P[16x16]^T (24 tcgen05.mma per stage, A from TMEM, P from smem).
 //   scores  T is read back once (tcgen05.ld), T2 = t^T Sinv t stays in a register, t is split and
 //           stored as the A operand of the second product.
 //   pass 2  the same tile is streamed again -- from L2, where pass 1 left it (evict_first now) --
 //           centred spectra go straight into the accumulator D[128x128] (tcgen05.st), the MMA warp issues
-//           D -= T * P[:, chunk] (6 MMAs per 128 columns, same smem copy of P read MN-major), threads
+//           D -= T * P[:, chunk] (6 MMAs per 128 columns, the same smem copy of P read MN-major), threads
 //           read D back and accumulate Q = sum r^2.
 // Only T2, Q and the decision go back to HBM.  All hand-offs are mbarriers; every wait is bounded.
 #include "ocm_common.cuh"
@@ -33,33 +44,30 @@ namespace ocm {
 namespace tc {
 
 constexpr int P_COLS = 1024;            // wavelengths (fixed: the loadings live in smem)
-constexpr int NCOMP = 16;               // MMA N of the projection (components padded to 16)
+constexpr int NCOMP = 16;               // MMA N of the projection / K of the reconstruction (components padded)
 constexpr int TILE_M = 128;             // spectra per tile = TMEM lanes
-constexpr int STAGE_COLS = 32;          // columns per cp.async stage
-constexpr int STAGE_PITCH = 36;         // floats; 144 B rows keep row-per-lane LDS.128 conflict free
-constexpr int NSTAGE = 5;               // ring depth
-constexpr int STAGES_PER_PASS = P_COLS / STAGE_COLS;        // 32
-constexpr int NABUF = 4;                // A-operand buffers (hi 32 cols + lo 32 cols each)
+constexpr int STAGE_COLS = 64;          // columns per cp.async stage = one 128-byte bf16 swizzle atom
+constexpr int STAGE_PITCH = 68;         // floats; 272 B rows keep row-per-lane LDS.128 conflict free
+constexpr int NSTAGE = 3;               // ring depth
+constexpr int STAGES_PER_PASS = P_COLS / STAGE_COLS;        // 16
+constexpr int NABUF = 2;                // A-operand buffers: 3 terms x 32 TMEM columns (64 bf16) each
 constexpr int D2_COLS = 128;            // columns per residual chunk
+constexpr int SUBS = D2_COLS / STAGE_COLS;                  // stages per residual chunk (2)
 constexpr int NCONV = 256;              // converter threads (8 warps)
 constexpr int NTHREADS = NCONV + 32;    // + MMA warp
+constexpr int NACC_MAIN = 4;            // accumulators of the (1,1) products (one per k-step of a stage)
+constexpr int NACC = NACC_MAIN + 5 * 2; // + two per cross product: consecutive MMAs never share an accumulator
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t TM_ABUF = 0;         // pass 1: [b*64, b*64+32) hi, [b*64+32, b*64+64) lo ; pass 2: D2 buffers [b*128, +128)
-constexpr uint32_t TM_THI = 256;        // split scores, A operand of pass 2 (16 cols each)
-constexpr uint32_t TM_TLO = 272;
-// Projection accumulators, 16 cols each.  The tensor core adds every product into the fp32 accumulator
-// with truncation, so 384 chained accumulations bias t by ~1e-5 (measured: T2 low by 2.2e-5).  The
-// hi*hi products therefore rotate over NACC accumulators (32 accumulations each) and the two small
-// cross terms go to their own accumulator; the converter thread adds the five with round-to-nearest.
-constexpr int NACC = 4;
-constexpr uint32_t TM_T = 288;          // [288 + 16*i), i < NACC: hi*hi ; i == NACC: lo*hi + hi*lo
+constexpr uint32_t TM_ABUF = 0;         // pass 1: buffer b at [96 b, 96 b + 96): term i at +32 i ; pass 2: D2 buffers [128 b, +128)
+constexpr uint32_t TM_T = 256;          // projection accumulators, 16 cols each: 4 main + 10 cross
+constexpr uint32_t TM_TS = 256 + 16 * NACC;                 // split scores: term i at +8 i (16 bf16 = 8 columns)
+static_assert(TM_TS + 24 <= 512, "TMEM column budget");
 
-constexpr size_t SM_P = (size_t)NCOMP * P_COLS * 4;                       // 65536 per copy
-constexpr size_t SM_STAGE = (size_t)TILE_M * STAGE_PITCH * 4;             // 18432
-constexpr size_t SM_OFF_PHI = 0;
-constexpr size_t SM_OFF_PLO = SM_P;
-constexpr size_t SM_OFF_RING = 2 * SM_P;
+constexpr size_t SM_PTERM = (size_t)NCOMP * P_COLS * 2;                   // 32768 per bf16 term
+constexpr size_t SM_STAGE = (size_t)TILE_M * STAGE_PITCH * 4;             // 34816
+constexpr size_t SM_OFF_P = 0;
+constexpr size_t SM_OFF_RING = 3 * SM_PTERM;
 constexpr size_t SM_OFF_MU = SM_OFF_RING + NSTAGE * SM_STAGE;
 constexpr size_t SM_OFF_S = SM_OFF_MU + P_COLS * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
@@ -67,8 +75,8 @@ constexpr size_t SM_OFF_BAR = SM_OFF_Q + TILE_M * 4;
 constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
 
 __device__ unsigned int g_tc_timeout = 0;
-__device__ float* g_tc_debug = nullptr;
-__device__ unsigned int g_tc_variant = 0;    // bring-up switches for the residual MMA (0 = production)      // optional [128][1024] dump of the residual of tile 0 (tests / bring-up)
+__device__ float* g_tc_debug = nullptr;      // optional [128][1024] dump of the residual of tile 0 (tests / bring-up)
+__device__ unsigned int g_tc_variant = 0;    // bring-up switches for the residual MMA (0 = production)
 
 // ---------------------------------------------------------------- PTX wrappers ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,21 +112,25 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem descriptor]
+// D[tmem] (+)= A[tmem] * B[smem descriptor], bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -132,21 +144,30 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// shared-memory matrix descriptor, 128B swizzle (SM100 UMMA SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64)).  MN-major WITHOUT swizzle turned out to be a
-// silent no-op for kind::tf32 on this part (bring-up, tools/tc_diag.py), hence the swizzled atom.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);   // layout_type 2 = SWIZZLE_128B
-}
-// instruction descriptor (UMMA InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_negate 13,
-// a_major 15, b_major 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// exact 3-way bf16 split of two fp32 values, packed as the tensor core wants them (low half = lower K index):
+// b1 = top 16 bits, r1 = x - b1 (exact), b2 = top 16 bits of r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2
+__device__ __forceinline__ void split3_pack(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+    const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+    w1 = __byte_perm(u0, u1, 0x7632);
+    const float r0 = x0 - __uint_as_float(u0 & 0xFFFF0000u), r1 = x1 - __uint_as_float(u1 & 0xFFFF0000u);
+    const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+    w2 = __byte_perm(v0, v1, 0x7632);
+    const float s0 = r0 - __uint_as_float(v0 & 0xFFFF0000u), s1 = r1 - __uint_as_float(v1 & 0xFFFF0000u);
+    w3 = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
 }
 
-static_assert(NACC == 4 && NABUF == 4, "the score read-back below is written for four main accumulators");
+// shared-memory matrix descriptor, 128B swizzle (SM100 UMMA SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type 2 = SWIZZLE_128B [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (UMMA InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13), a_negate 13,
+// a_major 15, b_major 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 struct Args {
     const float* X; int64_t n; int64_t ldx;
@@ -158,6 +179,9 @@ struct Args {
 // mbarrier slots
 enum { B_AFULL = 0, B_AFREE = NABUF, B_DFULL = 2 * NABUF, B_DREADY = 2 * NABUF + 2, B_TREADY = 2 * NABUF + 4,
        B_THFULL = 2 * NABUF + 5, B_COUNT = 2 * NABUF + 6 };
+
+static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one main accumulator per k-step of a stage");
+static_assert(STAGES_PER_PASS % NABUF == 0 && (P_COLS / D2_COLS) % 2 == 0, "buffer use counts per tile must be whole");
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(Args a) {
@@ -177,7 +201,7 @@ score_tc_kernel(Args a) {
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
         for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), NCONV * (D2_COLS / STAGE_COLS)); mbar_init(BAR(B_DREADY + b), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), NCONV * SUBS); mbar_init(BAR(B_DREADY + b), 1); }
         mbar_init(BAR(B_TREADY), 1);
         mbar_init(BAR(B_THFULL), TILE_M);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -186,22 +210,27 @@ score_tc_kernel(Args a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // loadings -> smem, split hi / lo, in the canonical 128B-swizzled atom: [col/32] atoms of 16 rows (= comps)
-    // x 128 B (= 32 cols), 16-byte chunk index XOR (comp % 8).  The SAME bytes are a K-major SW128 operand
-    // for the projection (rows = N = comps, K = cols) and an MN-major SW128 operand for the reconstruction
-    // (rows = K = comps, MN = cols), so one copy of P serves both products.
-    for (int idx = tid; idx < NCOMP * (P_COLS / 4); idx += NTHREADS) {
-        const int c = idx / (P_COLS / 4), j4 = idx % (P_COLS / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < a.A) v = *reinterpret_cast<const float4*>(a.P + (size_t)c * P_COLS + 4 * j4);
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
-        const size_t off = (size_t)(j4 >> 3) * 2048 + (size_t)c * 128 + (size_t)((j4 & 7) ^ (c & 7)) * 16;
-        *reinterpret_cast<float4*>(smem + SM_OFF_PHI + off) = hi;
-        *reinterpret_cast<float4*>(smem + SM_OFF_PLO + off) = lo;
+    // loadings -> smem: three bf16 terms, each in the canonical 128B-swizzled atom
+    //   [col/64] atoms of 16 rows (= components) x 128 B (= 64 bf16 columns), 16-byte chunk index XOR (comp % 8).
+    // The SAME bytes are a K-major SW128 operand for the projection (rows = N = components, K = columns) and an
+    // MN-major SW128 operand for the reconstruction (rows = K = components, MN = columns).
+    for (int idx = tid; idx < NCOMP * (P_COLS / 8); idx += NTHREADS) {
+        const int c = idx / (P_COLS / 8), j8 = idx % (P_COLS / 8);       // 8 columns = one 16-byte chunk
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (c < a.A) {
+            const float4 lo = *reinterpret_cast<const float4*>(a.P + (size_t)c * P_COLS + 8 * j8);
+            const float4 hi = *reinterpret_cast<const float4*>(a.P + (size_t)c * P_COLS + 8 * j8 + 4);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        }
+        uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split3_pack(v[2 * e], v[2 * e + 1], w1[e], w2[e], w3[e]);
+        const size_t off = (size_t)(j8 >> 3) * 2048 + (size_t)c * 128 + (size_t)((j8 & 7) ^ (c & 7)) * 16;
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 0 * SM_PTERM + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 1 * SM_PTERM + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 2 * SM_PTERM + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
     }
     for (int i = tid; i < P_COLS; i += NTHREADS) s_mu[i] = a.mu[i];
     for (int i = tid; i < NCOMP * NCOMP; i += NTHREADS) {
@@ -219,7 +248,7 @@ score_tc_kernel(Args a) {
         // converter warps
         // =====================================================================================
         const int row = 32 * (warp & 3) + lane;         // TMEM lane == spectrum inside the tile
-        const int half = warp >> 2;                     // which 16 columns of a 32-column stage
+        const int half = warp >> 2;                     // which 32 columns of a 64-column stage
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         uint64_t pol_keep, pol_stream;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
@@ -235,9 +264,9 @@ score_tc_kernel(Args a) {
                 const uint32_t dst0 = sb + (uint32_t)SM_OFF_RING + (uint32_t)(q % NSTAGE) * (uint32_t)SM_STAGE;
                 const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const int idx = tid + NCONV * i;
-                    const int r = idx >> 3, c4 = idx & 7;
+                    const int r = idx >> 4, c4 = idx & 15;
                     int64_t grow = row0 + r;
                     grow = grow < a.n ? grow : a.n - 1;
                     cp_async16_hint(dst0 + (uint32_t)(r * STAGE_PITCH * 4 + c4 * 16),
@@ -251,24 +280,26 @@ score_tc_kernel(Args a) {
 
         float t2_row = 0.f, q_acc = 0.f;
 
-        // residual chunk c2 of tile k back from TMEM: my lane, my 4 x 16 columns.  Buffer b = c2 & 1 is
-        // used 4 times per tile, so this is its (4k + c2/2)-th completion.
+        // residual chunk c2 of tile k back from TMEM: my lane, my 2 x 32 columns.  Buffer b = c2 & 1 is
+        // used (P_COLS / D2_COLS) / 2 = 4 times per tile, so this is its (4k + c2/2)-th completion.
         auto read_d2 = [&](int64_t k, int c2) {
             const int b = c2 & 1;
             mbar_wait(BAR(B_DREADY + b), (uint32_t)((4 * k + (c2 >> 1)) & 1));
             tc_fence_after();
 #pragma unroll
-            for (int sub = 0; sub < D2_COLS / STAGE_COLS; ++sub) {
-                uint32_t v[16];
-                tc_ld16(lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 16 * half), v);
+            for (int sub = 0; sub < SUBS; ++sub) {
+                uint32_t v[32];
+                const uint32_t addr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 32 * half);
+                tc_ld16(addr, v);
+                tc_ld16(addr + 16, v + 16);
                 tc_wait_ld();
                 if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        g_tc_debug[(size_t)row * P_COLS + c2 * D2_COLS + sub * STAGE_COLS + 16 * half + i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i)
+                        g_tc_debug[(size_t)row * P_COLS + c2 * D2_COLS + sub * STAGE_COLS + 32 * half + i] = __uint_as_float(v[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
+                for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
             }
             tc_fence_before();
         };
@@ -282,11 +313,11 @@ score_tc_kernel(Args a) {
             const int w = (int)(q % (2 * STAGES_PER_PASS));
             const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
             const float* st = reinterpret_cast<const float*>(smem + SM_OFF_RING + (size_t)(q % NSTAGE) * SM_STAGE) +
-                              row * STAGE_PITCH + 16 * half;
-            const float* mu = s_mu + chunk * STAGE_COLS + 16 * half;
-            float xc[16];
+                              row * STAGE_PITCH + 32 * half;
+            const float* mu = s_mu + chunk * STAGE_COLS + 32 * half;
+            float xc[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const float4 v = *reinterpret_cast<const float4*>(st + 4 * i);
                 const float4 m = *reinterpret_cast<const float4*>(mu + 4 * i);
                 xc[4 * i] = v.x - m.x; xc[4 * i + 1] = v.y - m.y; xc[4 * i + 2] = v.z - m.z; xc[4 * i + 3] = v.w - m.w;
@@ -294,17 +325,16 @@ score_tc_kernel(Args a) {
 
             if (pass == 0) {
                 const int b = chunk % NABUF;
-                // buffer b is used 8 times per tile: wait until the MMAs of its previous user retired
+                // buffer b is used STAGES_PER_PASS / NABUF = 8 times per tile: wait until the MMAs of its previous user retired
                 mbar_wait(BAR(B_AFREE + b), (uint32_t)(((8 * k + chunk / NABUF) & 1) ^ 1));
                 tc_fence_after();
-                uint32_t hi[16], lo[16];
+                uint32_t w1[16], w2[16], w3[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    hi[i] = __float_as_uint(xc[i]) & 0xFFFFE000u;
-                    lo[i] = __float_as_uint(xc[i] - __uint_as_float(hi[i]));
-                }
-                tc_st16(lane_addr + TM_ABUF + (uint32_t)(b * 64 + 16 * half), hi);
-                tc_st16(lane_addr + TM_ABUF + (uint32_t)(b * 64 + 32 + 16 * half), lo);
+                for (int i = 0; i < 16; ++i) split3_pack(xc[2 * i], xc[2 * i + 1], w1[i], w2[i], w3[i]);
+                const uint32_t abase = lane_addr + TM_ABUF + (uint32_t)(b * 96 + 16 * half);
+                tc_st16(abase, w1);
+                tc_st16(abase + 32, w2);
+                tc_st16(abase + 64, w3);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(BAR(B_AFULL + b));
@@ -316,17 +346,29 @@ score_tc_kernel(Args a) {
                     if (half == 0) {
                         float t[16];
                         {
-                            uint32_t m0[16], m1[16], m2[16], m3[16], cr[16];
+                            // small cross terms first (pairwise), then the four large (1,1) partial sums
+                            float cross[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) cross[i] = 0.f;
+#pragma unroll
+                            for (int g = 0; g < 5; ++g) {
+                                uint32_t c0[16], c1[16];
+                                tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g), c0);
+                                tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g + 1), c1);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
+                            }
+                            uint32_t m0[16], m1[16], m2[16], m3[16];
                             tc_ld16(lane_addr + TM_T + 0, m0);
                             tc_ld16(lane_addr + TM_T + 16, m1);
                             tc_ld16(lane_addr + TM_T + 32, m2);
                             tc_ld16(lane_addr + TM_T + 48, m3);
-                            tc_ld16(lane_addr + TM_T + 64, cr);
                             tc_wait_ld();
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
                                 t[i] = ((__uint_as_float(m0[i]) + __uint_as_float(m1[i])) +
-                                        (__uint_as_float(m2[i]) + __uint_as_float(m3[i]))) + __uint_as_float(cr[i]);
+                                        (__uint_as_float(m2[i]) + __uint_as_float(m3[i]))) + cross[i];
                         }
                         float t2 = 0.f;
 #pragma unroll
@@ -337,14 +379,12 @@ score_tc_kernel(Args a) {
                             t2 = fmaf(s, t[r], t2);
                         }
                         t2_row = t2;
-                        uint32_t thi[16], tlo[16];
+                        uint32_t s1[8], s2[8], s3[8];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            thi[i] = __float_as_uint(t[i]) & 0xFFFFE000u;
-                            tlo[i] = __float_as_uint(t[i] - __uint_as_float(thi[i]));
-                        }
-                        tc_st16(lane_addr + TM_THI, thi);
-                        tc_st16(lane_addr + TM_TLO, tlo);
+                        for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
+                        tc_st8(lane_addr + TM_TS, s1);
+                        tc_st8(lane_addr + TM_TS + 8, s2);
+                        tc_st8(lane_addr + TM_TS + 16, s3);
                         tc_wait_st();
                         tc_fence_before();
                         mbar_arrive(BAR(B_THFULL));
@@ -352,16 +392,18 @@ score_tc_kernel(Args a) {
                     q_acc = 0.f;
                 }
             } else {
-                const int c2 = chunk / (D2_COLS / STAGE_COLS), sub = chunk % (D2_COLS / STAGE_COLS);
+                const int c2 = chunk / SUBS, sub = chunk % SUBS;
                 const int b = c2 & 1;
-                uint32_t v[16];
+                uint32_t v[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(xc[i]);
-                tc_st16(lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 16 * half), v);
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(xc[i]);
+                const uint32_t daddr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 32 * half);
+                tc_st16(daddr, v);
+                tc_st16(daddr + 16, v + 16);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(BAR(B_DFULL + b));
-                if (sub == D2_COLS / STAGE_COLS - 1) {
+                if (sub == SUBS - 1) {
                     if (c2 >= 1) read_d2(k, c2 - 1);                      // previous chunk, overlapped with this chunk's MMAs
                     if (chunk == STAGES_PER_PASS - 1) {
                         read_d2(k, c2);
@@ -391,28 +433,30 @@ score_tc_kernel(Args a) {
         const unsigned int variant = g_tc_variant;
         const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, !(variant & 1u), !(variant & 4u));
         const uint32_t lbo2 = (variant & 2u) ? 1024u : 2048u, sbo2 = (variant & 2u) ? 2048u : 1024u;
-        const uint32_t sPhi = sb + (uint32_t)SM_OFF_PHI, sPlo = sb + (uint32_t)SM_OFF_PLO;
+        const uint32_t sP = sb + (uint32_t)SM_OFF_P;
+        // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
+        const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         for (int64_t k = 0; k < my_tiles; ++k) {
-            // ---- projection: T += A_chunk * P_chunk^T ------------------------------------------
+            // ---- projection: T += A_stage * P_stage^T ------------------------------------------
             for (int chunk = 0; chunk < STAGES_PER_PASS; ++chunk) {
                 const int b = chunk % NABUF;
                 if (lane == 0) {
                     mbar_wait(BAR(B_AFULL + b), (uint32_t)((8 * k + chunk / NABUF) & 1));
                     tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < STAGE_COLS / 8; ++ks) {
-                        const uint32_t a_hi = tmem + TM_ABUF + (uint32_t)(b * 64 + 8 * ks);
-                        const uint32_t a_lo = a_hi + 32;
-                        // K-major SW128: one 32-column atom per stage, K advances 32 B inside the atom,
+                    for (int ks = 0; ks < STAGE_COLS / 16; ++ks) {
+                        // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
                         // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
                         const uint32_t poff = (uint32_t)chunk * 2048u + (uint32_t)ks * 32u;
-                        const uint64_t d_hi = make_desc(sPhi + poff, 16, 1024);
-                        const uint64_t d_lo = make_desc(sPlo + poff, 16, 1024);
-                        const uint32_t t_main = tmem + TM_T + 16u * (uint32_t)(chunk % NACC);
-                        const uint32_t t_cross = tmem + TM_T + 16u * NACC;
-                        tc_mma_ts(t_main, a_hi, d_hi, IDESC1, (chunk >= NACC || ks != 0) ? 1u : 0u);
-                        tc_mma_ts(t_cross, a_lo, d_hi, IDESC1, (chunk | ks) != 0 ? 1u : 0u);
-                        tc_mma_ts(t_cross, a_hi, d_lo, IDESC1, 1);
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) {
+                            const uint32_t a_t = tmem + TM_ABUF + (uint32_t)(b * 96 + 32 * pa[m] + 8 * ks);
+                            const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, 16, 1024);
+                            // accumulator: (1,1) -> one per k-step; cross product m -> two, alternating with the k-step
+                            const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + (ks & 1));
+                            const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && ks < 2);
+                            tc_mma_ts(tmem + TM_T + 16u * acc, a_t, d_b, IDESC1, first ? 0u : 1u);
+                        }
                     }
                     tc_commit(BAR(B_AFREE + b));
                     if (chunk == STAGES_PER_PASS - 1) tc_commit(BAR(B_TREADY));
@@ -430,16 +474,13 @@ score_tc_kernel(Args a) {
                 if (lane == 0) {
                     mbar_wait(BAR(B_DFULL + b), (uint32_t)((4 * k + (c2 >> 1)) & 1));
                     tc_fence_after();
+                    // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
+                    const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 64)) * 2048u;
+                    const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
 #pragma unroll
-                    for (int ks = 0; ks < NCOMP / 8; ++ks) {
-                        // MN-major SW128: 32-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO)
-                        const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 32)) * 2048u + (uint32_t)ks * 1024u;
-                        const uint64_t d_hi = make_desc(sPhi + poff, lbo2, sbo2);
-                        const uint64_t d_lo = make_desc(sPlo + poff, lbo2, sbo2);
-                        const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
-                        tc_mma_ts(dst, tmem + TM_THI + 8 * ks, d_hi, IDESC2, 1);
-                        tc_mma_ts(dst, tmem + TM_TLO + 8 * ks, d_hi, IDESC2, 1);
-                        tc_mma_ts(dst, tmem + TM_THI + 8 * ks, d_lo, IDESC2, 1);
+                    for (int m = 0; m < 6; ++m) {
+                        const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, lbo2, sbo2);
+                        tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d_b, IDESC2, 1);
                     }
                     tc_commit(BAR(B_DREADY + b));
                 }
