@@ -38,6 +38,7 @@
 // Only T2, Q and the decision go back to HBM.  All hand-offs are mbarriers; every wait is bounded.
 #include "ocm_common.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace ocm {
@@ -46,15 +47,17 @@ namespace tc {
 constexpr int P_COLS = 1024;            // wavelengths (fixed: the loadings live in smem)
 constexpr int NCOMP = 16;               // MMA N of the projection / K of the reconstruction (components padded)
 constexpr int TILE_M = 128;             // spectra per tile = TMEM lanes
-constexpr int STAGE_COLS = 64;          // columns per cp.async stage = one 128-byte bf16 swizzle atom
-constexpr int STAGE_PITCH = 68;         // floats; 272 B rows keep row-per-lane LDS.128 conflict free
-constexpr int NSTAGE = 3;               // ring depth
+constexpr int STAGE_COLS = 64;          // columns per stage = one 128-byte bf16 swizzle atom of P = two TMA boxes of 32 floats
+constexpr int BOX_COLS = 32;            // TMA box: 128 rows x 32 floats (128 B rows, SWIZZLE_128B -> row-per-lane LDS.128 conflict free)
+constexpr int NSTAGE = 3;               // ring depth (96 KB in flight per SM)
 constexpr int STAGES_PER_PASS = P_COLS / STAGE_COLS;        // 16
 constexpr int NABUF = 2;                // A-operand buffers: 3 terms x 32 TMEM columns (64 bf16) each
 constexpr int D2_COLS = 128;            // columns per residual chunk
 constexpr int SUBS = D2_COLS / STAGE_COLS;                  // stages per residual chunk (2)
-constexpr int NCONV = 256;              // converter threads (8 warps)
-constexpr int NTHREADS = NCONV + 32;    // + MMA warp
+constexpr int NCONV = 512;              // converter threads (16 warps): TMEM lane = spectrum, 4 column quarters per stage
+constexpr int NQ = NCONV / TILE_M;      // column quarters
+constexpr int QCOLS = STAGE_COLS / NQ;  // 16 columns per thread per stage
+constexpr int NTHREADS = NCONV + 64;    // + TMA producer warp + MMA warp
 constexpr int NACC_MAIN = 4;            // accumulators of the (1,1) products (one per k-step of a stage)
 constexpr int NACC = NACC_MAIN + 5 * 2; // + two per cross product: consecutive MMAs never share an accumulator
 
@@ -65,13 +68,14 @@ constexpr uint32_t TM_TS = 256 + 16 * NACC;                 // split scores: ter
 static_assert(TM_TS + 24 <= 512, "TMEM column budget");
 
 constexpr size_t SM_PTERM = (size_t)NCOMP * P_COLS * 2;                   // 32768 per bf16 term
-constexpr size_t SM_STAGE = (size_t)TILE_M * STAGE_PITCH * 4;             // 34816
+constexpr size_t SM_BOX = (size_t)TILE_M * BOX_COLS * 4;                  // 16384
+constexpr size_t SM_STAGE = 2 * SM_BOX;                                   // 32768
 constexpr size_t SM_OFF_P = 0;
 constexpr size_t SM_OFF_RING = 3 * SM_PTERM;
 constexpr size_t SM_OFF_MU = SM_OFF_RING + NSTAGE * SM_STAGE;
 constexpr size_t SM_OFF_S = SM_OFF_MU + P_COLS * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
-constexpr size_t SM_OFF_BAR = SM_OFF_Q + TILE_M * 4;
+constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
 
 __device__ unsigned int g_tc_timeout = 0;
@@ -170,21 +174,32 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool
 }
 
 struct Args {
-    const float* X; int64_t n; int64_t ldx;
+    int64_t n;
     const float* mu; const float* P; const float* Sinv;
     int A; int rule; float ct, cq, dlim;
     float* T2; float* Q; uint8_t* accept;
 };
 
 // mbarrier slots
-enum { B_AFULL = 0, B_AFREE = NABUF, B_DFULL = 2 * NABUF, B_DREADY = 2 * NABUF + 2, B_TREADY = 2 * NABUF + 4,
-       B_THFULL = 2 * NABUF + 5, B_COUNT = 2 * NABUF + 6 };
+enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE + NABUF, B_DFULL = 2 * NSTAGE + 2 * NABUF,
+       B_DREADY = B_DFULL + 2, B_TREADY = B_DFULL + 4, B_THFULL = B_DFULL + 5, B_COUNT = B_DFULL + 6 };
 
 static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one main accumulator per k-step of a stage");
-static_assert(STAGES_PER_PASS % NABUF == 0 && (P_COLS / D2_COLS) % 2 == 0, "buffer use counts per tile must be whole");
+static_assert(NABUF == 2 && (STAGES_PER_PASS / NABUF) % 2 == 0 && ((P_COLS / D2_COLS) / 2) % 2 == 0,
+              "per-tile buffer use counts are even, so mbarrier parities depend on the position inside the tile only");
+static_assert(8 * B_COUNT + 8 <= 256, "barrier block");
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-score_tc_kernel(Args a) {
+score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_mu = reinterpret_cast<float*>(smem + SM_OFF_MU);
     float* s_S = reinterpret_cast<float*>(smem + SM_OFF_S);
@@ -197,16 +212,18 @@ score_tc_kernel(Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (a.n + TILE_M - 1) / TILE_M;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr int W_TMA = NCONV / 32, W_MMA = NCONV / 32 + 1;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), NCONV); }
         for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), NCONV * SUBS); mbar_init(BAR(B_DREADY + b), 1); }
         mbar_init(BAR(B_TREADY), 1);
         mbar_init(BAR(B_THFULL), TILE_M);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == NCONV / 32) {   // the MMA warp owns the TMEM allocation
+    if (warp == W_MMA) {   // the MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -248,183 +265,179 @@ score_tc_kernel(Args a) {
         // converter warps
         // =====================================================================================
         const int row = 32 * (warp & 3) + lane;         // TMEM lane == spectrum inside the tile
-        const int half = warp >> 2;                     // which 32 columns of a 64-column stage
+        const int qd = warp >> 2;                       // which 16 columns of a 64-column stage
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        uint64_t pol_keep, pol_stream;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-
-        const int64_t total_stages = my_tiles * 2 * STAGES_PER_PASS;
-        auto issue_stage = [&](int64_t q) {
-            if (q < total_stages) {
-                const int64_t k = q / (2 * STAGES_PER_PASS);
-                const int w = (int)(q % (2 * STAGES_PER_PASS));
-                const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
-                const int64_t row0 = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M;
-                const uint32_t dst0 = sb + (uint32_t)SM_OFF_RING + (uint32_t)(q % NSTAGE) * (uint32_t)SM_STAGE;
-                const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int idx = tid + NCONV * i;
-                    const int r = idx >> 4, c4 = idx & 15;
-                    int64_t grow = row0 + r;
-                    grow = grow < a.n ? grow : a.n - 1;
-                    cp_async16_hint(dst0 + (uint32_t)(r * STAGE_PITCH * 4 + c4 * 16),
-                                    a.X + grow * a.ldx + chunk * STAGE_COLS + 4 * c4, pol);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-
-        for (int s = 0; s < NSTAGE - 1; ++s) issue_stage(s);
+        // my 4 x 16 B inside the swizzled box: chunk c = 4 (qd & 1) + i lives at physical chunk c ^ (row % 8)
+        const uint32_t my_off = (uint32_t)(qd >> 1) * (uint32_t)SM_BOX + (uint32_t)row * 128u;
+        const int c_base = 4 * (qd & 1), rsw = row & 7;
 
         float t2_row = 0.f, q_acc = 0.f;
 
-        // residual chunk c2 of tile k back from TMEM: my lane, my 2 x 32 columns.  Buffer b = c2 & 1 is
-        // used (P_COLS / D2_COLS) / 2 = 4 times per tile, so this is its (4k + c2/2)-th completion.
+        // residual chunk c2 back from TMEM: my lane, my 2 x 16 columns (buffer b = c2 & 1, (c2/2)-th use in the tile)
         auto read_d2 = [&](int64_t k, int c2) {
             const int b = c2 & 1;
-            mbar_wait(BAR(B_DREADY + b), (uint32_t)((4 * k + (c2 >> 1)) & 1));
+            mbar_wait(BAR(B_DREADY + b), (uint32_t)((c2 >> 1) & 1));
             tc_fence_after();
+            uint32_t v[32];
+            const uint32_t addr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + QCOLS * qd);
+            tc_ld16(addr, v);
+            tc_ld16(addr + STAGE_COLS, v + 16);
+            tc_wait_ld();
+            if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
 #pragma unroll
-            for (int sub = 0; sub < SUBS; ++sub) {
-                uint32_t v[32];
-                const uint32_t addr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 32 * half);
-                tc_ld16(addr, v);
-                tc_ld16(addr + 16, v + 16);
-                tc_wait_ld();
-                if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        g_tc_debug[(size_t)row * P_COLS + c2 * D2_COLS + sub * STAGE_COLS + 32 * half + i] = __uint_as_float(v[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
+                for (int i = 0; i < 32; ++i)
+                    g_tc_debug[(size_t)row * P_COLS + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
             tc_fence_before();
         };
 
-        for (int64_t q = 0; q < total_stages; ++q) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");
-            named_bar_sync(1, NCONV);                 // stage q complete for everyone; slot (q-1)%NSTAGE is drained
-            issue_stage(q + NSTAGE - 1);
-
-            const int64_t k = q / (2 * STAGES_PER_PASS);
-            const int w = (int)(q % (2 * STAGES_PER_PASS));
-            const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
-            const float* st = reinterpret_cast<const float*>(smem + SM_OFF_RING + (size_t)(q % NSTAGE) * SM_STAGE) +
-                              row * STAGE_PITCH + 32 * half;
-            const float* mu = s_mu + chunk * STAGE_COLS + 32 * half;
-            float xc[32];
+        int slot = 0;
+        uint32_t ring_phase = 0;
+        for (int64_t k = 0; k < my_tiles; ++k) {
+            const uint32_t kpar = (uint32_t)(k & 1);
+#pragma unroll 1
+            for (int w = 0; w < 2 * STAGES_PER_PASS; ++w) {
+                const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
+                mbar_wait(BAR(B_FULL + slot), ring_phase);                 // TMA landed this stage
+                const uint8_t* st = smem + SM_OFF_RING + (size_t)slot * SM_STAGE + my_off;
+                const float* mu = s_mu + chunk * STAGE_COLS + QCOLS * qd;
+                float xc[QCOLS];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(st + 4 * i);
-                const float4 m = *reinterpret_cast<const float4*>(mu + 4 * i);
-                xc[4 * i] = v.x - m.x; xc[4 * i + 1] = v.y - m.y; xc[4 * i + 2] = v.z - m.z; xc[4 * i + 3] = v.w - m.w;
-            }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(st + (((c_base + i) ^ rsw) << 4));
+                    const float4 m = *reinterpret_cast<const float4*>(mu + 4 * i);
+                    xc[4 * i] = v.x - m.x; xc[4 * i + 1] = v.y - m.y; xc[4 * i + 2] = v.z - m.z; xc[4 * i + 3] = v.w - m.w;
+                }
+                mbar_arrive(BAR(B_EMPTY + slot));                          // my part of the stage is in registers
+                if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
 
-            if (pass == 0) {
-                const int b = chunk % NABUF;
-                // buffer b is used STAGES_PER_PASS / NABUF = 8 times per tile: wait until the MMAs of its previous user retired
-                mbar_wait(BAR(B_AFREE + b), (uint32_t)(((8 * k + chunk / NABUF) & 1) ^ 1));
-                tc_fence_after();
-                uint32_t w1[16], w2[16], w3[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) split3_pack(xc[2 * i], xc[2 * i + 1], w1[i], w2[i], w3[i]);
-                const uint32_t abase = lane_addr + TM_ABUF + (uint32_t)(b * 96 + 16 * half);
-                tc_st16(abase, w1);
-                tc_st16(abase + 32, w2);
-                tc_st16(abase + 64, w3);
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(BAR(B_AFULL + b));
-
-                if (chunk == STAGES_PER_PASS - 1) {
-                    // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
-                    mbar_wait(BAR(B_TREADY), (uint32_t)(k & 1));
+                if (pass == 0) {
+                    const int b = chunk & 1;
+                    mbar_wait(BAR(B_AFREE + b), (uint32_t)(((chunk >> 1) & 1) ^ 1));   // MMAs of the buffer's previous user retired
                     tc_fence_after();
-                    if (half == 0) {
-                        float t[16];
-                        {
-                            // small cross terms first (pairwise), then the four large (1,1) partial sums
-                            float cross[16];
+                    uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) cross[i] = 0.f;
+                    for (int i = 0; i < 8; ++i) split3_pack(xc[2 * i], xc[2 * i + 1], w1[i], w2[i], w3[i]);
+                    const uint32_t abase = lane_addr + TM_ABUF + (uint32_t)(b * 96 + 8 * qd);
+                    tc_st8(abase, w1);
+                    tc_st8(abase + 32, w2);
+                    tc_st8(abase + 64, w3);
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(BAR(B_AFULL + b));
+
+                    if (chunk == STAGES_PER_PASS - 1) {
+                        // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
+                        mbar_wait(BAR(B_TREADY), kpar);
+                        tc_fence_after();
+                        if (qd == 0) {
+                            float t[16];
+                            {
+                                // small cross terms first (pairwise), then the four large (1,1) partial sums
+                                float cross[16];
 #pragma unroll
-                            for (int g = 0; g < 5; ++g) {
-                                uint32_t c0[16], c1[16];
-                                tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g), c0);
-                                tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g + 1), c1);
+                                for (int i = 0; i < 16; ++i) cross[i] = 0.f;
+#pragma unroll
+                                for (int g = 0; g < 5; ++g) {
+                                    uint32_t c0[16], c1[16];
+                                    tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g), c0);
+                                    tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g + 1), c1);
+                                    tc_wait_ld();
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
+                                }
+                                uint32_t m0[16], m1[16];
+                                tc_ld16(lane_addr + TM_T + 0, m0);
+                                tc_ld16(lane_addr + TM_T + 16, m1);
                                 tc_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
+                                for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
+                                tc_ld16(lane_addr + TM_T + 32, m0);
+                                tc_ld16(lane_addr + TM_T + 48, m1);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
                             }
-                            uint32_t m0[16], m1[16], m2[16], m3[16];
-                            tc_ld16(lane_addr + TM_T + 0, m0);
-                            tc_ld16(lane_addr + TM_T + 16, m1);
-                            tc_ld16(lane_addr + TM_T + 32, m2);
-                            tc_ld16(lane_addr + TM_T + 48, m3);
-                            tc_wait_ld();
+                            float t2 = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                t[i] = ((__uint_as_float(m0[i]) + __uint_as_float(m1[i])) +
-                                        (__uint_as_float(m2[i]) + __uint_as_float(m3[i]))) + cross[i];
+                            for (int r = 0; r < NCOMP; ++r) {
+                                float s = 0.f;
+#pragma unroll
+                                for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
+                                t2 = fmaf(s, t[r], t2);
+                            }
+                            t2_row = t2;
+                            uint32_t s1[8], s2[8], s3[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
+                            tc_st8(lane_addr + TM_TS, s1);
+                            tc_st8(lane_addr + TM_TS + 8, s2);
+                            tc_st8(lane_addr + TM_TS + 16, s3);
+                            tc_wait_st();
+                            tc_fence_before();
+                            mbar_arrive(BAR(B_THFULL));
                         }
-                        float t2 = 0.f;
-#pragma unroll
-                        for (int r = 0; r < NCOMP; ++r) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
-                            t2 = fmaf(s, t[r], t2);
-                        }
-                        t2_row = t2;
-                        uint32_t s1[8], s2[8], s3[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
-                        tc_st8(lane_addr + TM_TS, s1);
-                        tc_st8(lane_addr + TM_TS + 8, s2);
-                        tc_st8(lane_addr + TM_TS + 16, s3);
-                        tc_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(BAR(B_THFULL));
+                        q_acc = 0.f;
                     }
-                    q_acc = 0.f;
-                }
-            } else {
-                const int c2 = chunk / SUBS, sub = chunk % SUBS;
-                const int b = c2 & 1;
-                uint32_t v[32];
+                } else {
+                    const int c2 = chunk / SUBS, sub = chunk % SUBS;
+                    const int b = c2 & 1;
+                    uint32_t v[QCOLS];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(xc[i]);
-                const uint32_t daddr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + 32 * half);
-                tc_st16(daddr, v);
-                tc_st16(daddr + 16, v + 16);
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(BAR(B_DFULL + b));
-                if (sub == SUBS - 1) {
-                    if (c2 >= 1) read_d2(k, c2 - 1);                      // previous chunk, overlapped with this chunk's MMAs
-                    if (chunk == STAGES_PER_PASS - 1) {
-                        read_d2(k, c2);
-                        // combine the two column halves of each spectrum, decide, write back
-                        if (half == 1) s_q[row] = q_acc;
-                        named_bar_sync(2, NCONV);
-                        if (half == 0) {
-                            const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
-                            if (grow < a.n) {
-                                const float qq = q_acc + s_q[row];
-                                if (a.T2) a.T2[grow] = t2_row;
-                                if (a.Q) a.Q[grow] = qq;
-                                if (a.accept) a.accept[grow] = rule_distance(a.rule, t2_row * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
+                    for (int i = 0; i < QCOLS; ++i) v[i] = __float_as_uint(xc[i]);
+                    tc_st16(lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + QCOLS * qd), v);
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(BAR(B_DFULL + b));
+                    if (sub == SUBS - 1) {
+                        if (c2 >= 1) read_d2(k, c2 - 1);                      // previous chunk, overlapped with this chunk's MMAs
+                        if (chunk == STAGES_PER_PASS - 1) {
+                            read_d2(k, c2);
+                            // combine the four column quarters of each spectrum, decide, write back
+                            if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
+                            named_bar_sync(2, NCONV);
+                            if (qd == 0) {
+                                const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
+                                if (grow < a.n) {
+                                    const float qq = (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
+                                    if (a.T2) a.T2[grow] = t2_row;
+                                    if (a.Q) a.Q[grow] = qq;
+                                    if (a.accept) a.accept[grow] = rule_distance(a.rule, t2_row * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
+                                }
                             }
+                            named_bar_sync(2, NCONV);                         // s_q reusable
                         }
-                        named_bar_sync(2, NCONV);                         // s_q reusable
                     }
                 }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp == W_TMA) {
+        // =====================================================================================
+        // TMA producer: one lane streams the tile twice (pass 1 keeps it in L2, pass 2 lets it go)
+        // =====================================================================================
+        if (lane == 0) {
+            uint64_t pol_keep, pol_stream;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            int slot = 0;
+            uint32_t ring_phase = 0;
+            for (int64_t k = 0; k < my_tiles; ++k) {
+                const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
+                for (int w = 0; w < 2 * STAGES_PER_PASS; ++w) {
+                    const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
+                    mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1);           // all converters drained the slot
+                    mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
+                    const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
+                    const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
+                    tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
+                    tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
+                    if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // =====================================================================================
         // MMA warp: one elected lane issues, the warp stays converged
@@ -439,9 +452,9 @@ score_tc_kernel(Args a) {
         for (int64_t k = 0; k < my_tiles; ++k) {
             // ---- projection: T += A_stage * P_stage^T ------------------------------------------
             for (int chunk = 0; chunk < STAGES_PER_PASS; ++chunk) {
-                const int b = chunk % NABUF;
+                const int b = chunk & 1;
                 if (lane == 0) {
-                    mbar_wait(BAR(B_AFULL + b), (uint32_t)((8 * k + chunk / NABUF) & 1));
+                    mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < STAGE_COLS / 16; ++ks) {
@@ -472,7 +485,7 @@ score_tc_kernel(Args a) {
             for (int c2 = 0; c2 < P_COLS / D2_COLS; ++c2) {
                 const int b = c2 & 1;
                 if (lane == 0) {
-                    mbar_wait(BAR(B_DFULL + b), (uint32_t)((4 * k + (c2 >> 1)) & 1));
+                    mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
                     tc_fence_after();
                     // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
                     const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 64)) * 2048u;
@@ -492,9 +505,40 @@ score_tc_kernel(Args a) {
     // ---- teardown -----------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == NCONV / 32) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
+}
+
+// ---- host side: TMA descriptor of the spectra matrix ---------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int64_t ldx) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return e != cudaSuccess ? (int)e : (int)cudaErrorNotSupported;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)P_COLS, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BOX_COLS, (cuuint32_t)TILE_M};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return (int)cudaErrorInvalidValue;
+    }
+    return 0;
 }
 
 }  // namespace tc
@@ -524,12 +568,16 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
                 "tensor-core path needs p == 1024, n_components <= 16, no fused SNV");
     OCM_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0,
                 OCM_EALIGN, "X rows and P must be 16-byte aligned");
-    tc::Args a{X, n, ldx, mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
+    OCM_REQUIRE(n < (1ll << 31) - tc::TILE_M, OCM_ELIMIT, "row count must fit the 32-bit TMA coordinate");
+    CUtensorMap tmap;
+    int rc = tc::make_tensor_map(&tmap, X, n, ldx);
+    if (rc) return rc;
+    tc::Args a{n, mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
     OCM_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
     int64_t blocks = sm_count();
     if (blocks > ntiles) blocks = ntiles;
-    tc::score_tc_kernel<<<(unsigned)blocks, tc::NTHREADS, tc::SM_TOTAL, (cudaStream_t)stream>>>(a);
+    tc::score_tc_kernel<<<(unsigned)blocks, tc::NTHREADS, tc::SM_TOTAL, (cudaStream_t)stream>>>(tmap, a);
     return check_launch("score_tc_kernel");
 }
 
