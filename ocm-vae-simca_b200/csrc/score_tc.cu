@@ -116,13 +116,24 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem descriptor], bf16 inputs, fp32 accumulate
+// D[tmem] (+)= A[tmem] * B[smem descriptor], bf16 inputs, fp32 accumulate.  Called by the WHOLE (converged) MMA
+// warp; one elected lane issues.  Keeping the control flow warp-uniform lets the compiler hold descriptors and
+// addresses in uniform registers -- with an `if (lane == 0)` branch around it every operand went through R2UR
+// and the issue loop ran at ~100 cycles per MMA (ncu: converters waiting on the A-buffer-free barrier).
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -453,51 +464,42 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             // ---- projection: T += A_stage * P_stage^T ------------------------------------------
             for (int chunk = 0; chunk < STAGES_PER_PASS; ++chunk) {
                 const int b = chunk & 1;
-                if (lane == 0) {
-                    mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < STAGE_COLS / 16; ++ks) {
-                        // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
-                        // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
-                        const uint32_t poff = (uint32_t)chunk * 2048u + (uint32_t)ks * 32u;
-#pragma unroll
-                        for (int m = 0; m < 6; ++m) {
-                            const uint32_t a_t = tmem + TM_ABUF + (uint32_t)(b * 96 + 32 * pa[m] + 8 * ks);
-                            const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, 16, 1024);
-                            // accumulator: (1,1) -> one per k-step; cross product m -> two, alternating with the k-step
-                            const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + (ks & 1));
-                            const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && ks < 2);
-                            tc_mma_ts(tmem + TM_T + 16u * acc, a_t, d_b, IDESC1, first ? 0u : 1u);
-                        }
-                    }
-                    tc_commit(BAR(B_AFREE + b));
-                    if (chunk == STAGES_PER_PASS - 1) tc_commit(BAR(B_TREADY));
-                }
-                __syncwarp();
-            }
-            // ---- residual: D = xc - T * P ----------------------------------------------------------
-            if (lane == 0) {
-                mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
+                mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
                 tc_fence_after();
-            }
-            __syncwarp();
-            for (int c2 = 0; c2 < P_COLS / D2_COLS; ++c2) {
-                const int b = c2 & 1;
-                if (lane == 0) {
-                    mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
-                    tc_fence_after();
-                    // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
-                    const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 64)) * 2048u;
-                    const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
+#pragma unroll
+                for (int ks = 0; ks < STAGE_COLS / 16; ++ks) {
+                    // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
+                    // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
+                    const uint32_t poff = (uint32_t)chunk * 2048u + (uint32_t)ks * 32u;
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
-                        const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, lbo2, sbo2);
-                        tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d_b, IDESC2, 1);
+                        const uint32_t a_t = tmem + TM_ABUF + (uint32_t)(b * 96 + 32 * pa[m] + 8 * ks);
+                        const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, 16, 1024);
+                        // accumulator: (1,1) -> one per k-step; cross product m -> two, alternating with the k-step
+                        const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + (ks & 1));
+                        const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && ks < 2);
+                        tc_mma_ts(tmem + TM_T + 16u * acc, a_t, d_b, IDESC1, first ? 0u : 1u);
                     }
-                    tc_commit(BAR(B_DREADY + b));
                 }
-                __syncwarp();
+                tc_commit_elect(BAR(B_AFREE + b));
+                if (chunk == STAGES_PER_PASS - 1) tc_commit_elect(BAR(B_TREADY));
+            }
+            // ---- residual: D = xc - T * P ----------------------------------------------------------
+            mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
+            tc_fence_after();
+            for (int c2 = 0; c2 < P_COLS / D2_COLS; ++c2) {
+                const int b = c2 & 1;
+                mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
+                tc_fence_after();
+                // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
+                const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 64)) * 2048u;
+                const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, lbo2, sbo2);
+                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d_b, IDESC2, 1);
+                }
+                tc_commit_elect(BAR(B_DREADY + b));
             }
         }
     }
