@@ -14,7 +14,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libocm_simca_b200.so")
+LIB_PATH = os.environ.get("OCM_SIMCA_LIB") or os.path.join(PKG_DIR, "libocm_simca_b200.so")   # override: A/B builds
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
