@@ -57,7 +57,8 @@ constexpr int SUBS = D2_COLS / STAGE_COLS;                  // stages per residu
 constexpr int NCONV = 512;              // converter threads (16 warps): TMEM lane = spectrum, 4 column quarters per stage
 constexpr int NQ = NCONV / TILE_M;      // column quarters
 constexpr int QCOLS = STAGE_COLS / NQ;  // 16 columns per thread per stage
-constexpr int NTHREADS = NCONV + 64;    // + TMA producer warp + MMA warp
+constexpr int NMMAW = 2;                // MMA-issuing warps (disjoint accumulators; the issue loop of ONE warp was the bottleneck)
+constexpr int NTHREADS = NCONV + 32 + 32 * NMMAW;   // + TMA producer warp + MMA warps
 constexpr int NACC_MAIN = 4;            // accumulators of the (1,1) products (one per k-step of a stage)
 constexpr int NACC = NACC_MAIN + 5 * 2; // + two per cross product: consecutive MMAs never share an accumulator
 
@@ -253,18 +254,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (a.n + TILE_M - 1) / TILE_M;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    constexpr int W_TMA = NCONV / 32, W_MMA = NCONV / 32 + 1;
+    constexpr int W_TMA = NCONV / 32, W_MMA = NCONV / 32 + 1;   // MMA warps: W_MMA .. W_MMA + NMMAW - 1
+    static_assert(NMMAW == 2 && P_COLS / D2_COLS % NMMAW == 0, "MMA warp j owns residual buffer j");
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), NCONV); }
-        for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), 1); }
+        for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), NMMAW); }
         for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), NCONV * SUBS); mbar_init(BAR(B_DREADY + b), 1); }
-        mbar_init(BAR(B_TREADY), 1);
+        mbar_init(BAR(B_TREADY), NMMAW);
         mbar_init(BAR(B_THFULL), TILE_M);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == W_MMA) {   // the MMA warp owns the TMEM allocation
+    if (warp == W_MMA) {   // the first MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -484,8 +486,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         __syncwarp();
     } else {
         // =====================================================================================
-        // MMA warp: one elected lane issues, the warp stays converged
+        // MMA warps: NMMAW warps, each converged, one elected lane issues.  Warp j owns k-steps {2j, 2j+1} of every
+        // projection stage (its own accumulators) and the residual chunks with buffer b == j, so every phase of a
+        // buffer's barriers is waited on by ONE warp in order (a parity wait issued a phase early returns at once).
         // =====================================================================================
+        const int mw = warp - W_MMA;                                        // 0 or 1
         constexpr uint32_t IDESC1 = make_idesc(TILE_M, NCOMP, false, false);
         const unsigned int variant = DEBUG ? g_tc_variant : 0u;
         const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, !(variant & 1u), !(variant & 4u));
@@ -499,39 +504,38 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 const int b = chunk & 1;
                 mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
                 tc_fence_after();
+                // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
+                // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
+                const uint64_t d0 = make_desc(sP + (uint32_t)chunk * 2048u, 16, 1024);
 #pragma unroll
-                for (int ks = 0; ks < STAGE_COLS / 16; ++ks) {
-                    // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
-                    // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
-                    const uint32_t poff = (uint32_t)chunk * 2048u + (uint32_t)ks * 32u;
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int ks = 2 * mw + kk;
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
                         const uint32_t a_t = tmem + TM_ABUF + (uint32_t)(b * 96 + 32 * pa[m] + 8 * ks);
-                        const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, 16, 1024);
-                        // accumulator: (1,1) -> one per k-step; cross product m -> two, alternating with the k-step
-                        const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + (ks & 1));
-                        const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && ks < 2);
+                        const uint64_t d_b = d0 + (uint64_t)(((uint32_t)pb[m] * (uint32_t)SM_PTERM + (uint32_t)ks * 32u) >> 4);
+                        // accumulator: (1,1) -> one per k-step; cross product m -> one per MMA warp
+                        const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + mw);
+                        const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && kk == 0);
                         tc_mma_ts(tmem + TM_T + 16u * acc, a_t, d_b, IDESC1, first ? 0u : 1u);
                     }
                 }
                 tc_commit_elect(BAR(B_AFREE + b));
                 if (chunk == STAGES_PER_PASS - 1) tc_commit_elect(BAR(B_TREADY));
             }
-            // ---- residual: D = xc - T * P ----------------------------------------------------------
+            // ---- residual: D = xc - T * P (chunks with buffer b == mw) ------------------------------
             mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
             tc_fence_after();
-            for (int c2 = 0; c2 < P_COLS / D2_COLS; ++c2) {
+            for (int c2 = mw; c2 < P_COLS / D2_COLS; c2 += NMMAW) {
                 const int b = c2 & 1;
                 mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
-                const uint32_t poff = (uint32_t)(c2 * (D2_COLS / 64)) * 2048u;
+                const uint64_t d0 = make_desc(sP + (uint32_t)(c2 * (D2_COLS / 64)) * 2048u, lbo2, sbo2);
                 const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
 #pragma unroll
-                for (int m = 0; m < 6; ++m) {
-                    const uint64_t d_b = make_desc(sP + (uint32_t)pb[m] * (uint32_t)SM_PTERM + poff, lbo2, sbo2);
-                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d_b, IDESC2, 1);
-                }
+                for (int m = 0; m < 6; ++m)
+                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * (uint32_t)SM_PTERM) >> 4), IDESC2, 1);
                 tc_commit_elect(BAR(B_DREADY + b));
             }
         }
