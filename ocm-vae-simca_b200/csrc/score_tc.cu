@@ -59,16 +59,23 @@ constexpr int NQ = NCONV / TILE_M;      // column quarters
 constexpr int QCOLS = STAGE_COLS / NQ;  // 16 columns per thread per stage
 constexpr int NMMAW = 2;                // MMA-issuing warps (disjoint accumulators; the issue loop of ONE warp was the bottleneck)
 constexpr int NTHREADS = NCONV + 32 + 32 * NMMAW;   // + TMA producer warp + MMA warps
-constexpr int NACC_MAIN = 4;            // accumulators of the (1,1) products (one per k-step of a stage)
-constexpr int NACC = NACC_MAIN + 5 * 2; // + two per cross product: consecutive MMAs never share an accumulator
+constexpr int NACC_MAIN = 4;            // accumulators of the A-term-1 products (one per k-step of a stage)
 
-// TMEM column map (512 columns allocated)
+// TMEM column map (512 columns allocated; base address 0 because the CTA owns the whole TMEM of its SM)
 constexpr uint32_t TM_ABUF = 0;         // pass 1: buffer b at [96 b, 96 b + 96): term i at +32 i ; pass 2: D2 buffers [128 b, +128)
-constexpr uint32_t TM_T = 256;          // projection accumulators, 16 cols each: 4 main + 10 cross
-constexpr uint32_t TM_TS = 256 + 16 * NACC;                 // split scores: term i at +8 i (16 bf16 = 8 columns)
+// Projection accumulators.  The three bf16 terms of P are stacked along N in shared memory, so ONE MMA per A term
+// covers several products:  A1 x [P1;P2;P3] (N=48) -> D1 = [(1,1) | (1,2) | (1,3)],  A2 x [P1;P2] (N=32) -> D2,
+// A3 x [P1] (N=16) -> D3.  D1 rotates over the 4 k-steps of a stage (16 chained accumulations per tile: the
+// tensor core adds into fp32 with truncation), D2 / D3 exist once per MMA warp.  [192, 256) overlaps the pass-2
+// residual buffer 1, which is only live after these accumulators have been read back.
+constexpr uint32_t TM_D1 = 192;         // + 48 ks
+constexpr uint32_t TM_D2 = 384;         // + 32 mw
+constexpr uint32_t TM_D3 = 448;         // + 16 mw
+constexpr uint32_t TM_TS = 480;         // split scores: term i at +8 i (16 bf16 = 8 columns)
 static_assert(TM_TS + 24 <= 512, "TMEM column budget");
 
-constexpr size_t SM_PTERM = (size_t)NCOMP * P_COLS * 2;                   // 32768 per bf16 term
+constexpr size_t SM_PATOM = 3 * NCOMP * 128;                              // 6144: one 64-column atom, 48 rows = 3 terms x 16 components
+constexpr size_t SM_PTERM = (size_t)NCOMP * P_COLS * 2;                   // 32768 bytes per bf16 term (all atoms)
 constexpr size_t SM_BOX = (size_t)TILE_M * BOX_COLS * 4;                  // 16384
 constexpr size_t SM_STAGE = 2 * SM_BOX;                                   // 32768
 constexpr size_t SM_OFF_P = 0;
@@ -225,7 +232,7 @@ struct Args {
 enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE + NABUF, B_DFULL = 2 * NSTAGE + 2 * NABUF,
        B_DREADY = B_DFULL + 2, B_TREADY = B_DFULL + 4, B_THFULL = B_DFULL + 5, B_COUNT = B_DFULL + 6 };
 
-static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one main accumulator per k-step of a stage");
+static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one D1 accumulator per k-step of a stage");
 static_assert(NABUF == 2 && (STAGES_PER_PASS / NABUF) % 2 == 0 && ((P_COLS / D2_COLS) / 2) % 2 == 0,
               "per-tile buffer use counts are even, so mbarrier parities depend on the position inside the tile only");
 static_assert(8 * B_COUNT + 8 <= 256, "barrier block");
@@ -270,8 +277,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // loadings -> smem: three bf16 terms, each in the canonical 128B-swizzled atom
-    //   [col/64] atoms of 16 rows (= components) x 128 B (= 64 bf16 columns), 16-byte chunk index XOR (comp % 8).
+    // loadings -> smem: three bf16 terms stacked along the row axis of the canonical 128B-swizzled atom
+    //   [col/64] atoms of 48 rows (= term*16 + component) x 128 B (= 64 bf16 columns), 16-byte chunk index XOR (row % 8).
     // The SAME bytes are a K-major SW128 operand for the projection (rows = N = components, K = columns) and an
     // MN-major SW128 operand for the reconstruction (rows = K = components, MN = columns).
     for (int idx = tid; idx < NCOMP * (P_COLS / 8); idx += NTHREADS) {
@@ -287,10 +294,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split3_pack(v[2 * e], v[2 * e + 1], w1[e], w2[e], w3[e]);
-        const size_t off = (size_t)(j8 >> 3) * 2048 + (size_t)c * 128 + (size_t)((j8 & 7) ^ (c & 7)) * 16;
-        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 0 * SM_PTERM + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 1 * SM_PTERM + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-        *reinterpret_cast<uint4*>(smem + SM_OFF_P + 2 * SM_PTERM + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+        // atom (64 columns) -> row = term * 16 + component (128 B) -> 16-byte chunk XOR (row % 8)
+        const size_t off = (size_t)(j8 >> 3) * SM_PATOM + (size_t)c * 128 + (size_t)((j8 & 7) ^ (c & 7)) * 16;
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 2048) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 4096) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
     }
     for (int i = tid; i < P_COLS; i += NTHREADS) s_mu[i] = a.mu[i];
     for (int i = tid; i < NCOMP * NCOMP; i += NTHREADS) {
@@ -301,7 +309,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
+    // The CTA is alone on its SM (shared-memory footprint) and allocates all 512 columns, so the base is 0; using
+    // the constant keeps every TMEM address an immediate in the MMA issue loop.  Anything else is flagged.
+    if (*s_tmem != 0u && tid == 0) atomicExch(&g_tc_timeout, 2u);
+    constexpr uint32_t tmem = 0u;
 
     if (warp < NCONV / 32) {
         // =====================================================================================
@@ -381,27 +392,31 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                         if (qd == 0) {
                             float t[16];
                             {
-                                // small cross terms first (pairwise), then the four large (1,1) partial sums
+                                // small cross products first, then the four large (1,1) partial sums, all round-to-nearest
                                 float cross[16];
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) cross[i] = 0.f;
-#pragma unroll
-                                for (int g = 0; g < 5; ++g) {
+                                auto add_pair = [&](uint32_t c0a, uint32_t c1a) {
                                     uint32_t c0[16], c1[16];
-                                    tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g), c0);
-                                    tc_ld16(lane_addr + TM_T + 16u * (uint32_t)(NACC_MAIN + 2 * g + 1), c1);
+                                    tc_ld16(lane_addr + c0a, c0);
+                                    tc_ld16(lane_addr + c1a, c1);
                                     tc_wait_ld();
 #pragma unroll
                                     for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
-                                }
+                                };
+#pragma unroll
+                                for (int ks = 0; ks < NACC_MAIN; ++ks) add_pair(TM_D1 + 48u * ks + 16u, TM_D1 + 48u * ks + 32u);   // (1,2) (1,3)
+                                add_pair(TM_D2 + 0u, TM_D2 + 16u);            // (2,1) (2,2) of MMA warp 0
+                                add_pair(TM_D2 + 32u, TM_D2 + 48u);           //                 MMA warp 1
+                                add_pair(TM_D3 + 0u, TM_D3 + 16u);            // (3,1) of both MMA warps
                                 uint32_t m0[16], m1[16];
-                                tc_ld16(lane_addr + TM_T + 0, m0);
-                                tc_ld16(lane_addr + TM_T + 16, m1);
+                                tc_ld16(lane_addr + TM_D1 + 0u, m0);
+                                tc_ld16(lane_addr + TM_D1 + 48u, m1);
                                 tc_wait_ld();
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
-                                tc_ld16(lane_addr + TM_T + 32, m0);
-                                tc_ld16(lane_addr + TM_T + 48, m1);
+                                tc_ld16(lane_addr + TM_D1 + 96u, m0);
+                                tc_ld16(lane_addr + TM_D1 + 144u, m1);
                                 tc_wait_ld();
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
@@ -491,34 +506,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         // buffer's barriers is waited on by ONE warp in order (a parity wait issued a phase early returns at once).
         // =====================================================================================
         const int mw = warp - W_MMA;                                        // 0 or 1
-        constexpr uint32_t IDESC1 = make_idesc(TILE_M, NCOMP, false, false);
+        constexpr uint32_t IDESC_N48 = make_idesc(TILE_M, 48, false, false);
+        constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false);
+        constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false);
         const unsigned int variant = DEBUG ? g_tc_variant : 0u;
         const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, !(variant & 1u), !(variant & 4u));
-        const uint32_t lbo2 = (variant & 2u) ? 1024u : 2048u, sbo2 = (variant & 2u) ? 2048u : 1024u;
+        const uint32_t lbo2 = (variant & 2u) ? 1024u : (uint32_t)SM_PATOM, sbo2 = (variant & 2u) ? (uint32_t)SM_PATOM : 1024u;
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         for (int64_t k = 0; k < my_tiles; ++k) {
-            // ---- projection: T += A_stage * P_stage^T ------------------------------------------
+            // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
             for (int chunk = 0; chunk < STAGES_PER_PASS; ++chunk) {
                 const int b = chunk & 1;
                 mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
                 tc_fence_after();
-                // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom,
-                // 8-row (component) groups 1024 B apart; LBO is not used by swizzled K-major layouts
-                const uint64_t d0 = make_desc(sP + (uint32_t)chunk * 2048u, 16, 1024);
+                // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
+                // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
+                const uint64_t d0 = make_desc(sP + (uint32_t)chunk * (uint32_t)SM_PATOM, 16, 1024);
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     const int ks = 2 * mw + kk;
-#pragma unroll
-                    for (int m = 0; m < 6; ++m) {
-                        const uint32_t a_t = tmem + TM_ABUF + (uint32_t)(b * 96 + 32 * pa[m] + 8 * ks);
-                        const uint64_t d_b = d0 + (uint64_t)(((uint32_t)pb[m] * (uint32_t)SM_PTERM + (uint32_t)ks * 32u) >> 4);
-                        // accumulator: (1,1) -> one per k-step; cross product m -> one per MMA warp
-                        const uint32_t acc = (m == 0) ? (uint32_t)ks : (uint32_t)(NACC_MAIN + 2 * (m - 1) + mw);
-                        const uint32_t first = (m == 0) ? (chunk == 0) : (chunk == 0 && kk == 0);
-                        tc_mma_ts(tmem + TM_T + 16u * acc, a_t, d_b, IDESC1, first ? 0u : 1u);
-                    }
+                    const uint64_t d_b = d0 + (uint64_t)(((uint32_t)ks * 32u) >> 4);
+                    const uint32_t a0 = tmem + TM_ABUF + (uint32_t)(b * 96 + 8 * ks);
+                    tc_mma_ts(tmem + TM_D1 + 48u * (uint32_t)ks, a0, d_b, IDESC_N48, chunk != 0 ? 1u : 0u);
+                    tc_mma_ts(tmem + TM_D2 + 32u * (uint32_t)mw, a0 + 32, d_b, IDESC_N32, (chunk != 0 || kk != 0) ? 1u : 0u);
+                    tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (chunk != 0 || kk != 0) ? 1u : 0u);
                 }
                 tc_commit_elect(BAR(B_AFREE + b));
                 if (chunk == STAGES_PER_PASS - 1) tc_commit_elect(BAR(B_TREADY));
@@ -530,12 +543,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 const int b = c2 & 1;
                 mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
                 tc_fence_after();
-                // MN-major SW128: 64-column atoms 2048 B apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in one MMA
-                const uint64_t d0 = make_desc(sP + (uint32_t)(c2 * (D2_COLS / 64)) * 2048u, lbo2, sbo2);
+                // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
+                // one MMA; the B term selects the 16-row slab (2048 B) inside the atom
+                const uint64_t d0 = make_desc(sP + (uint32_t)(c2 * (D2_COLS / 64)) * (uint32_t)SM_PATOM, lbo2, sbo2);
                 const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
 #pragma unroll
                 for (int m = 0; m < 6; ++m)
-                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * (uint32_t)SM_PTERM) >> 4), IDESC2, 1);
+                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * 2048u) >> 4), IDESC2, 1);
                 tc_commit_elect(BAR(B_DREADY + b));
             }
         }
