@@ -246,7 +246,7 @@ def main():
     if args.force_simt:
         kernel_name = "score_simt_kernel"
     elif lib.ocm_simca_score_tc_supported(rows, p, p, A, 0, C_void(X)):
-        kernel_name = "score_tc_kernel (tcgen05)"
+        kernel_name = "score_tc_kernel<false> (tcgen05.mma kind::f16 bf16x3, TMEM operands, TMA ring)"
     elif lib.ocm_simca_score_rowteam_supported(rows, p, p, A, 0, C_void(X)):
         kernel_name = f"score_rowteam_kernel<{A},{p // 128 if p <= 1024 else 8},{128 if p <= 1024 else 256}> (FFMA2)"
     else:

@@ -600,17 +600,15 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int64_t 
 }  // namespace tc
 }  // namespace ocm
 
-// Shape gate of the dispatcher.  STATUS (round 1): the projection half of this kernel is verified against
-// the oracle (T2 within 1e-5), the reconstruction half is not yet correct -- kind::tf32 accepts an MN-major
-// B operand only in the SWIZZLE_128B_BASE32B layout, which cannot share one smem copy of P with the K-major
-// projection operand, and two copies (256 KB) do not fit.  Until the bf16x3 variant lands the dispatcher
-// never selects this kernel: the gate below returns 0 unless OCM_EXPERIMENTAL_TC=1 is set (bring-up only).
+// Shape gate of the dispatcher: fp32 rows of 1024 wavelengths, n_components <= 16, 16-byte aligned rows, no fused
+// SNV, and enough rows to fill the machine (below ~2 tiles per SM the FP32-pipe kernels have less fixed cost:
+// this kernel stages 96 KB of loadings per CTA).  OCM_DISABLE_TC=1 forces the FP32-pipe kernels (A/B runs).
 extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X) {
-    static const bool enabled = [] { const char* e = getenv("OCM_EXPERIMENTAL_TC"); return e && e[0] == '1'; }();
-    if (!enabled) return 0;
+    static const bool disabled = [] { const char* e = getenv("OCM_DISABLE_TC"); return e && e[0] == '1'; }();
+    if (disabled) return 0;
     if (snv || p != ocm::tc::P_COLS || A < 1 || A > ocm::tc::NCOMP) return 0;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
-    if (n < 4096) return 0;                  // small batches: the FP32-pipe kernels have less fixed cost
+    if (n < 32768 || n >= (1ll << 31) - ocm::tc::TILE_M) return 0;
     return 1;
 }
 

@@ -243,6 +243,7 @@ def test_rowteam_kernel_matches_generic_and_oracle(torch):
             mu32, P32 = pca.arrays32()
             prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
             assert native.lib().ocm_simca_score_rowteam_supported(4099, p, p, A, 0, C.c_void_p(X.data_ptr())) == 1
+            assert native.lib().ocm_simca_score_tc_supported(4099, p, p, A, 0, C.c_void_p(X.data_ptr())) == 0   # too few rows
             outs = []
             for fn in (native.lib().ocm_simca_score_rowteam_f32, None):
                 T2 = torch.empty(4099, device=dev); Q = torch.empty(4099, device=dev)
