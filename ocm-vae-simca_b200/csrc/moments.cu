@@ -10,6 +10,8 @@
 // folds never materialise copies of X.
 #include "ocm_common.cuh"
 
+#include <stdlib.h>
+
 namespace ocm {
 
 // ---------------------------------------------------------------- column sums -----------
@@ -109,6 +111,125 @@ gram_f64_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------- fp64 tensor-core Gram ---
+// The same contraction on the FP64 tensor pipe (DMMA, mma.sync m8n8k4 f64): 128x128 output tile per CTA
+// (upper-triangle tiles only), 8 warps of 64x32, 16-row K stages double-buffered in shared memory, the next
+// stage prefetched into registers while the current one is multiplied.  Why fp64 and not the tcgen05 low-precision
+// kinds: the 5th-gen tensor core adds into its fp32 accumulator with truncation, which biases a chain of k
+// accumulations by ~k * 2^-25 relative (measured in score_tc.cu: 384 chained MMAs -> -1.1e-5).  On strongly
+// correlated spectra that bias is structured (sign-consistent products) and of the size of the small
+// eigenvalues a SIMCA model needs (lambda_20 / lambda_1 ~ 2e-4), and an on-chip fp64 tile (128x256 doubles =
+// 256 KB) does not exist to flush short chains into.  DMMA keeps every product and sum in fp64.
+constexpr int DT = 128;        // tile edge
+constexpr int DK = 16;         // rows per stage
+constexpr int DPITCH = DT + 4; // doubles; +32 B per row keeps the fragment LDS.64 conflict free
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+gram_dmma_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx,
+                 int64_t n, int p, const double* __restrict__ shift, double* __restrict__ G,
+                 int64_t rows_per_split) {
+    extern __shared__ __align__(16) double sm_d[];
+    double (*As)[DK][DPITCH] = reinterpret_cast<double (*)[DK][DPITCH]>(sm_d);
+    double (*Bs)[DK][DPITCH] = reinterpret_cast<double (*)[DK][DPITCH]>(sm_d + 2 * DK * DPITCH);
+
+    const int nt = (p + DT - 1) / DT;
+    int t = blockIdx.x, ti = 0;
+    while (t >= nt - ti) { t -= nt - ti; ++ti; }
+    const int tj = ti + t;
+    const int i0 = ti * DT, j0 = tj * DT;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tq = lane & 3;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(n, r_begin + rows_per_split);
+
+    // loader: 2 x (4 consecutive columns) of the A block and of the B block per thread and stage
+    const int lk0 = tid >> 5, lc = (tid & 31) * 4;           // rows lk0 and lk0 + 8, columns lc .. lc+3
+    double shA[4], shB[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        shA[e] = (shift && i0 + lc + e < p) ? shift[i0 + lc + e] : 0.0;
+        shB[e] = (shift && j0 + lc + e < p) ? shift[j0 + lc + e] : 0.0;
+    }
+    double ra[2][4], rb[2][4];
+    auto fetch = [&](int64_t r0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t r = r0 + lk0 + 8 * h;
+            if (r < r_end) {
+                const int64_t row = row_idx ? row_idx[r] : r;
+                const T* xr = X + row * ldx;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ra[h][e] = (i0 + lc + e < p) ? (double)xr[i0 + lc + e] - shA[e] : 0.0;
+                    rb[h][e] = (j0 + lc + e < p) ? (double)xr[j0 + lc + e] - shB[e] : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ra[h][e] = rb[h][e] = 0.0;
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double2* da = reinterpret_cast<double2*>(&As[buf][lk0 + 8 * h][lc]);
+            double2* db = reinterpret_cast<double2*>(&Bs[buf][lk0 + 8 * h][lc]);
+            da[0] = make_double2(ra[h][0], ra[h][1]); da[1] = make_double2(ra[h][2], ra[h][3]);
+            db[0] = make_double2(rb[h][0], rb[h][1]); db[1] = make_double2(rb[h][2], rb[h][3]);
+        }
+    };
+
+    fetch(r_begin);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += DK) {
+        const bool more = r0 + DK < r_end;
+        if (more) fetch(r0 + DK);                             // global loads in flight under the MMAs
+#pragma unroll
+        for (int k4 = 0; k4 < DK / 4; ++k4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) a[mt] = As[buf][4 * k4 + tq][64 * wm + 8 * mt + g];
+#pragma unroll
+            for (int ntl = 0; ntl < 4; ++ntl) b[ntl] = Bs[buf][4 * k4 + tq][32 * wn + 8 * ntl + g];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int ntl = 0; ntl < 4; ++ntl) dmma884(acc[mt][ntl][0], acc[mt][ntl][1], a[mt], b[ntl]);
+        }
+        if (more) stash(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+        const int i = i0 + 64 * wm + 8 * mt + g;
+        if (i >= p) continue;
+#pragma unroll
+        for (int ntl = 0; ntl < 4; ++ntl)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + 32 * wn + 8 * ntl + 2 * tq + e;
+                if (j < p && j >= i) atomicAdd(G + (int64_t)i * p + j, acc[mt][ntl][e]);
+            }
+    }
+}
+
 // ---------------------------------------------------------------- combine ---------------
 struct PartsArgs {
     int ngroups;
@@ -164,6 +285,26 @@ int gram_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_
               const double* shift, double* G, void* stream) {
     if (n == 0) return 0;
     OCM_REQUIRE(X && G && n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    static const bool simple = [] { const char* e = getenv("OCM_GRAM_SIMPLE"); return e && e[0] == '1'; }();
+    if (!simple && p >= 96 && n >= 64) {
+        // FP64 tensor-pipe kernel: 128x128 tiles, one CTA per SM, K split to fill the machine
+        const int ntd = (p + DT - 1) / DT;
+        const int tiles = ntd * (ntd + 1) / 2;
+        int64_t splits = sm_count() / tiles;
+        if (splits < 1) splits = 1;
+        const int64_t max_splits = (n + 255) / 256;
+        if (splits > max_splits) splits = max_splits;
+        int64_t rps = (n + splits - 1) / splits;
+        rps = (rps + DK - 1) / DK * DK;
+        splits = (n + rps - 1) / rps;
+        const size_t smem = sizeof(double) * 4 * DK * DPITCH;
+        auto kern = gram_dmma_kernel<T>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        dim3 grid(tiles, 1, (unsigned)splits);
+        kern<<<grid, 256, smem, (cudaStream_t)stream>>>(X, ldx, row_idx, n, p, shift, G, rps);
+        return check_launch("gram_dmma_kernel");
+    }
     const int nt = (p + GT - 1) / GT;
     const int ntiles = nt * (nt + 1) / 2;
     // enough K-splits to fill the machine ~2 waves, at least 64 rows per split

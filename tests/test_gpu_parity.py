@@ -172,6 +172,27 @@ def test_cv_param_grid_and_lv1(torch):
         assert abs(o["sens"] - r["sens"]) < 1.0 and abs(o["spec"] - r["spec"]) < 2.0
 
 
+def test_gram_kernels_match_numpy(torch):
+    """fp64 Gram (FP64 tensor-pipe DMMA kernel and the small-problem kernel) against numpy: ragged p, row gather,
+    fp32 and fp64 rows, K-splits, accumulate-into semantics."""
+    rng = np.random.default_rng(3)
+    dev = torch.device("cuda")
+    for n, p, dt in ((300, 700, np.float64), (1030, 1050, np.float32), (5000, 128, np.float32), (64, 96, np.float64),
+                     (40, 33, np.float32), (2000, 2048, np.float32)):
+        X = (rng.normal(1.0, 0.3, (n, p)) * np.linspace(0.5, 2.0, p)).astype(dt)
+        idx = np.sort(rng.choice(n, size=max(3, (2 * n) // 3), replace=False))
+        shift = X[idx].mean(0).astype(np.float64)
+        Xd = torch.as_tensor(X, device=dev)
+        for rows in (None, idx):
+            Xs = (X if rows is None else X[rows]).astype(np.float64) - shift
+            ref = np.triu(Xs.T @ Xs)
+            G = engine.gram(Xd, None if rows is None else engine.index_tensor(rows, dev), torch.as_tensor(shift, device=dev))
+            got = np.triu(G.cpu().numpy())
+            np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-10 * np.abs(ref).max(), err_msg=f"n={n} p={p}")
+            G2 = engine.gram(Xd, None if rows is None else engine.index_tensor(rows, dev), torch.as_tensor(shift, device=dev), out=G)
+            np.testing.assert_allclose(np.triu(G2.cpu().numpy()), 2 * ref, rtol=1e-11, atol=1e-10 * np.abs(ref).max())
+
+
 def test_preprocess_kernels(torch):
     rng = np.random.default_rng(0)
     for p in (700, 1024, 1050):
