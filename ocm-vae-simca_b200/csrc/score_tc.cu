@@ -1,5 +1,5 @@
 // Fused SIMCA scoring on the 5th-generation tensor cores (tcgen05 + TMEM) -- the bulk path for
-// config 3 (fp32 rows, p = 1024, A <= 16).
+// config 3 (fp32 rows, 64 <= p <= 1152, A <= 16; benchmarked at p = 1024).
 //
 // Why tensor cores for an HBM-bound op: per spectrum 2*p*A FMAs ride on 4*p bytes, so the FP32 pipe
 // and HBM balance at A = 10; FP32 operand delivery caps the FP32-pipe kernel (score_rowteam.cu) near
@@ -44,13 +44,12 @@
 namespace ocm {
 namespace tc {
 
-constexpr int P_COLS = 1024;            // wavelengths (fixed: the loadings live in smem)
+constexpr int P_MAX = 1152;             // most wavelengths supported (the loadings live in smem: 96 B per column)
 constexpr int NCOMP = 16;               // MMA N of the projection / K of the reconstruction (components padded)
 constexpr int TILE_M = 128;             // spectra per tile = TMEM lanes
 constexpr int STAGE_COLS = 64;          // columns per stage = one 128-byte bf16 swizzle atom of P = two TMA boxes of 32 floats
 constexpr int BOX_COLS = 32;            // TMA box: 128 rows x 32 floats (128 B rows, SWIZZLE_128B -> row-per-lane LDS.128 conflict free)
 constexpr int NSTAGE = 3;               // ring depth (96 KB in flight per SM)
-constexpr int STAGES_PER_PASS = P_COLS / STAGE_COLS;        // 16
 constexpr int NABUF = 2;                // A-operand buffers: 3 terms x 32 TMEM columns (64 bf16) each
 constexpr int D2_COLS = 128;            // columns per residual chunk
 constexpr int SUBS = D2_COLS / STAGE_COLS;                  // stages per residual chunk (2)
@@ -75,13 +74,12 @@ constexpr uint32_t TM_TS = 480;         // split scores: term i at +8 i (16 bf16
 static_assert(TM_TS + 24 <= 512, "TMEM column budget");
 
 constexpr size_t SM_PATOM = 3 * NCOMP * 128;                              // 6144: one 64-column atom, 48 rows = 3 terms x 16 components
-constexpr size_t SM_PTERM = (size_t)NCOMP * P_COLS * 2;                   // 32768 bytes per bf16 term (all atoms)
 constexpr size_t SM_BOX = (size_t)TILE_M * BOX_COLS * 4;                  // 16384
 constexpr size_t SM_STAGE = 2 * SM_BOX;                                   // 32768
 constexpr size_t SM_OFF_P = 0;
-constexpr size_t SM_OFF_RING = 3 * SM_PTERM;
+constexpr size_t SM_OFF_RING = (size_t)(P_MAX / 64) * SM_PATOM;            // 110592
 constexpr size_t SM_OFF_MU = SM_OFF_RING + NSTAGE * SM_STAGE;
-constexpr size_t SM_OFF_S = SM_OFF_MU + P_COLS * 4;
+constexpr size_t SM_OFF_S = SM_OFF_MU + P_MAX * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
@@ -223,6 +221,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool
 
 struct Args {
     int64_t n;
+    int p;            // wavelengths (multiple of 4, <= P_MAX); processed as ns stages of 64 columns, zero padded
+    int ns;           // stages per pass = 2 * ceil(p / 128)
     const float* mu; const float* P; const float* Sinv;
     int A; int rule; float ct, cq, dlim;
     float* T2; float* Q; uint8_t* accept;
@@ -233,8 +233,7 @@ enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE 
        B_DREADY = B_DFULL + 2, B_TREADY = B_DFULL + 4, B_THFULL = B_DFULL + 5, B_COUNT = B_DFULL + 6 };
 
 static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one D1 accumulator per k-step of a stage");
-static_assert(NABUF == 2 && (STAGES_PER_PASS / NABUF) % 2 == 0 && ((P_COLS / D2_COLS) / 2) % 2 == 0,
-              "per-tile buffer use counts are even, so mbarrier parities depend on the position inside the tile only");
+static_assert(NABUF == 2 && P_MAX % D2_COLS == 0, "two A buffers; residual chunks of 128 columns");
 static_assert(8 * B_COUNT + 8 <= 256, "barrier block");
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -262,7 +261,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     const int64_t ntiles = (a.n + TILE_M - 1) / TILE_M;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr int W_TMA = NCONV / 32, W_MMA = NCONV / 32 + 1;   // MMA warps: W_MMA .. W_MMA + NMMAW - 1
-    static_assert(NMMAW == 2 && P_COLS / D2_COLS % NMMAW == 0, "MMA warp j owns residual buffer j");
+    static_assert(NMMAW == 2, "MMA warp j owns residual buffer j");
+    const int ns = a.ns, nc = a.ns / SUBS;                      // stages per pass, residual chunks per tile
+    // mbarrier phase of the u-th use of a buffer is u & 1.  Use counts: A buffer b, tile k, stage `chunk`:
+    // k*ns/2 + chunk/2 ; residual buffer b, tile k, chunk c2: k*ceil-or-floor(nc/2) + c2/2.
+    auto a_use = [&](int64_t k, int chunk) { return (uint32_t)((k * (ns >> 1) + (chunk >> 1)) & 1); };
+    auto d_use = [&](int64_t k, int c2) { return (uint32_t)((k * ((nc + 1 - (c2 & 1)) >> 1) + (c2 >> 1)) & 1); };
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
@@ -281,15 +285,21 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     //   [col/64] atoms of 48 rows (= term*16 + component) x 128 B (= 64 bf16 columns), 16-byte chunk index XOR (row % 8).
     // The SAME bytes are a K-major SW128 operand for the projection (rows = N = components, K = columns) and an
     // MN-major SW128 operand for the reconstruction (rows = K = components, MN = columns).
-    for (int idx = tid; idx < NCOMP * (P_COLS / 8); idx += NTHREADS) {
-        const int c = idx / (P_COLS / 8), j8 = idx % (P_COLS / 8);       // 8 columns = one 16-byte chunk
+    const int nchunk16 = ns * 8;                                          // 16-byte chunks per row of the padded P
+    for (int idx = tid; idx < NCOMP * nchunk16; idx += NTHREADS) {
+        const int c = idx / nchunk16, j8 = idx % nchunk16;              // 8 columns = one 16-byte chunk
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (c < a.A) {
-            const float4 lo = *reinterpret_cast<const float4*>(a.P + (size_t)c * P_COLS + 8 * j8);
-            const float4 hi = *reinterpret_cast<const float4*>(a.P + (size_t)c * P_COLS + 8 * j8 + 4);
-            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        if (c < a.A) {                                                   // columns >= p and components >= A are zero
+            if (8 * j8 + 4 <= a.p) {
+                const float4 lo = *reinterpret_cast<const float4*>(a.P + (size_t)c * a.p + 8 * j8);
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+            }
+            if (8 * j8 + 8 <= a.p) {
+                const float4 hi = *reinterpret_cast<const float4*>(a.P + (size_t)c * a.p + 8 * j8 + 4);
+                v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            }
         }
         uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
@@ -300,7 +310,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 2048) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
         *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 4096) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
     }
-    for (int i = tid; i < P_COLS; i += NTHREADS) s_mu[i] = a.mu[i];
+    for (int i = tid; i < ns * STAGE_COLS; i += NTHREADS) s_mu[i] = i < a.p ? a.mu[i] : 0.f;
     for (int i = tid; i < NCOMP * NCOMP; i += NTHREADS) {
         const int r = i / NCOMP, c = i % NCOMP;
         s_S[i] = (r < a.A && c < a.A) ? a.Sinv[r * a.A + c] : 0.f;
@@ -330,7 +340,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         // residual chunk c2 back from TMEM: my lane, my 2 x 16 columns (buffer b = c2 & 1, (c2/2)-th use in the tile)
         auto read_d2 = [&](int64_t k, int c2) {
             const int b = c2 & 1;
-            mbar_wait(BAR(B_DREADY + b), (uint32_t)((c2 >> 1) & 1));
+            mbar_wait(BAR(B_DREADY + b), d_use(k, c2));
             tc_fence_after();
             uint32_t v[32];
             const uint32_t addr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + QCOLS * qd);
@@ -341,7 +351,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        g_tc_debug[(size_t)row * P_COLS + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);
+                        g_tc_debug[(size_t)row * 1024 + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);   // p == 1024 only
                 }
             }
 #pragma unroll
@@ -354,8 +364,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         for (int64_t k = 0; k < my_tiles; ++k) {
             const uint32_t kpar = (uint32_t)(k & 1);
 #pragma unroll 1
-            for (int w = 0; w < 2 * STAGES_PER_PASS; ++w) {
-                const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
+            for (int w = 0; w < 2 * ns; ++w) {
+                const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
                 mbar_wait(BAR(B_FULL + slot), ring_phase);                 // TMA landed this stage
                 const uint8_t* st = smem + SM_OFF_RING + (size_t)slot * SM_STAGE + my_off;
                 const float* mu = s_mu + chunk * STAGE_COLS + QCOLS * qd;
@@ -372,7 +382,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 
                 if (pass == 0) {
                     const int b = chunk & 1;
-                    mbar_wait(BAR(B_AFREE + b), (uint32_t)(((chunk >> 1) & 1) ^ 1));   // MMAs of the buffer's previous user retired
+                    mbar_wait(BAR(B_AFREE + b), a_use(k, chunk) ^ 1u);          // MMAs of the buffer's previous user retired
                     tc_fence_after();
                     uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
@@ -385,7 +395,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     tc_fence_before();
                     mbar_arrive(BAR(B_AFULL + b));
 
-                    if (chunk == STAGES_PER_PASS - 1) {
+                    if (chunk == ns - 1) {
                         // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
                         mbar_wait(BAR(B_TREADY), kpar);
                         tc_fence_after();
@@ -454,7 +464,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     mbar_arrive(BAR(B_DFULL + b));
                     if (sub == SUBS - 1) {
                         if (c2 >= 1) read_d2(k, c2 - 1);                      // previous chunk, overlapped with this chunk's MMAs
-                        if (chunk == STAGES_PER_PASS - 1) {
+                        if (chunk == ns - 1) {
                             read_d2(k, c2);
                             // combine the four column quarters of each spectrum, decide, write back
                             if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
@@ -486,8 +496,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             uint32_t ring_phase = 0;
             for (int64_t k = 0; k < my_tiles; ++k) {
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
-                for (int w = 0; w < 2 * STAGES_PER_PASS; ++w) {
-                    const int pass = w / STAGES_PER_PASS, chunk = w % STAGES_PER_PASS;
+                for (int w = 0; w < 2 * ns; ++w) {
+                    const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
                     mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1);           // all converters drained the slot
                     mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
                     const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
@@ -517,9 +527,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         for (int64_t k = 0; k < my_tiles; ++k) {
             // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
-            for (int chunk = 0; chunk < STAGES_PER_PASS; ++chunk) {
+            for (int chunk = 0; chunk < ns; ++chunk) {
                 const int b = chunk & 1;
-                mbar_wait(BAR(B_AFULL + b), (uint32_t)((chunk >> 1) & 1));
+                mbar_wait(BAR(B_AFULL + b), a_use(k, chunk));
                 tc_fence_after();
                 // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
                 // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
@@ -534,14 +544,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (chunk != 0 || kk != 0) ? 1u : 0u);
                 }
                 tc_commit_elect(BAR(B_AFREE + b));
-                if (chunk == STAGES_PER_PASS - 1) tc_commit_elect(BAR(B_TREADY));
+                if (chunk == ns - 1) tc_commit_elect(BAR(B_TREADY));
             }
             // ---- residual: D = xc - T * P (chunks with buffer b == mw) ------------------------------
             mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
             tc_fence_after();
-            for (int c2 = mw; c2 < P_COLS / D2_COLS; c2 += NMMAW) {
+            for (int c2 = mw; c2 < nc; c2 += NMMAW) {
                 const int b = c2 & 1;
-                mbar_wait(BAR(B_DFULL + b), (uint32_t)((c2 >> 1) & 1));
+                mbar_wait(BAR(B_DFULL + b), d_use(k, c2));
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
                 // one MMA; the B term selects the 16-row slab (2048 B) inside the atom
@@ -571,7 +581,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int64_t ldx) {
+static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, int64_t ldx) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -583,7 +593,7 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int64_t 
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)P_COLS, (cuuint64_t)n};
+    const cuuint64_t dims[2] = {(cuuint64_t)p, (cuuint64_t)n};      // columns >= p of a box are zero filled
     const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)BOX_COLS, (cuuint32_t)TILE_M};
     const cuuint32_t estr[2] = {1, 1};
@@ -606,7 +616,7 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int64_t 
 extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X) {
     static const bool disabled = [] { const char* e = getenv("OCM_DISABLE_TC"); return e && e[0] == '1'; }();
     if (disabled) return 0;
-    if (snv || p != ocm::tc::P_COLS || A < 1 || A > ocm::tc::NCOMP) return 0;
+    if (snv || p < 64 || p > ocm::tc::P_MAX || (p & 3) || A < 1 || A > ocm::tc::NCOMP) return 0;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
     if (n < 32768 || n >= (1ll << 31) - ocm::tc::TILE_M) return 0;
     return 1;
@@ -618,15 +628,15 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     using namespace ocm;
     if (n == 0) return 0;
     OCM_REQUIRE(X && mu && P && Sinv && hp, OCM_EINVAL, "NULL buffer");
-    OCM_REQUIRE(p == tc::P_COLS && hp->A >= 1 && hp->A <= tc::NCOMP && !hp->snv, OCM_ELIMIT,
-                "tensor-core path needs p == 1024, n_components <= 16, no fused SNV");
+    OCM_REQUIRE(p >= 64 && p <= tc::P_MAX && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc::NCOMP && !hp->snv, OCM_ELIMIT,
+                "tensor-core path needs 64 <= p <= 1152 (multiple of 4), n_components <= 16, no fused SNV");
     OCM_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0,
                 OCM_EALIGN, "X rows and P must be 16-byte aligned");
     OCM_REQUIRE(n < (1ll << 31) - tc::TILE_M, OCM_ELIMIT, "row count must fit the 32-bit TMA coordinate");
     CUtensorMap tmap;
-    int rc = tc::make_tensor_map(&tmap, X, n, ldx);
+    int rc = tc::make_tensor_map(&tmap, X, n, p, ldx);
     if (rc) return rc;
-    tc::Args a{n, mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
+    tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
     const bool debug = tc::h_debug_on || tc::h_variant != 0;  // bring-up only; the production kernel has neither hook
     auto kern = debug ? tc::score_tc_kernel<true> : tc::score_tc_kernel<false>;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));

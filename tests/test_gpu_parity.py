@@ -294,9 +294,9 @@ def test_tensor_core_kernel_matches_oracle(torch):
     """tcgen05 scoring kernel (p = 1024, bf16x3 split products, TMEM operands) against the fp64 arithmetic:
     ragged tile counts, several component counts, full Sinv, and no bounded mbarrier wait may time out."""
     dev = torch.device("cuda")
-    p = 1024
     lib = native.lib()
-    for n, A in ((128 * 150 + 77, 10), (5000, 16), (4097, 3), (128 * 300, 1)):
+    for n, A, p in ((128 * 150 + 77, 10, 1024), (5000, 16, 1024), (4097, 3, 1024), (128 * 300, 1, 1024),
+                    (20000, 5, 700), (9000, 12, 1052), (30000, 10, 1152), (3000, 4, 64), (7000, 8, 520)):
         X = synth.make_spectra_device(n, p, dev, seed=n % 97 + A)
         pca = engine.fit_pca(X[:2000].contiguous(), None, A)
         Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev)) + (1e-3 if A > 1 else 0.0)
@@ -313,8 +313,8 @@ def test_tensor_core_kernel_matches_oracle(torch):
         model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
         T2r, Qr = so.score(model, X.double().cpu().numpy())
         # T2 = sum of A terms of order 1: a row whose scores happen to be ~0 has no relative precision
-        np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=RTOL, atol=2e-7 * A, err_msg=f"n={n} A={A}")
-        np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=RTOL, err_msg=f"n={n} A={A}")
+        np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=RTOL, atol=2e-7 * A, err_msg=f"n={n} A={A} p={p}")
+        np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=RTOL, err_msg=f"n={n} A={A} p={p}")
         d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
         assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
 
