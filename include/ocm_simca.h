@@ -87,6 +87,12 @@ int ocm_cov_from_parts_f64(const double* Gparts, const double* sparts, const int
                            const double* shift, double* C, double* mean, double* delta,
                            void* stream);
 
+/* ---- a4 / a12: batched symmetric eigensolver for small matrices (m <= 64), parallel cyclic Jacobi, one CTA per
+ * matrix.  H [batch][m][m] fp64 (symmetrised internally), evals [batch][m] DESCENDING, evecs [batch][m][m] with
+ * eigenvectors as COLUMNS in the same order.  It is the Rayleigh-Ritz step of the batched subspace iteration that
+ * fits all CV folds at once (replaces the per-(fold, LV) SVDs of utils/CVSIMCA.py:183-184). */
+int ocm_eigh_small_f64(const double* H, int32_t m, int32_t batch, double* evals, double* evecs, void* stream);
+
 /* ---- a5 / a9 / a10: fused scoring (replaces pca.transform + inverse_transform + the
  * two reductions of SIMCA.predict / SIMCA.transform, utils/SIMCA.py:101-145) -----------
  * For each row x:  [optional SNV] -> xc = x - mu -> t = P xc -> r = xc - P^T t ->

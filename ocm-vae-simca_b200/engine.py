@@ -193,6 +193,79 @@ def eigh_topk(Cm, k):
     return w, V
 
 
+def eigh_small(H):
+    """Batched eigen-decomposition of small symmetric fp64 matrices [B, m, m], m <= 64 (ocm_eigh_small_f64: parallel
+    Jacobi, one CTA per matrix).  Returns (w [B, m] descending, U [B, m, m] eigenvectors as columns)."""
+    torch = _torch()
+    H = H.contiguous()
+    B, m, _ = H.shape
+    w = torch.empty((B, m), dtype=torch.float64, device=H.device)
+    U = torch.empty((B, m, m), dtype=torch.float64, device=H.device)
+    native.check(native.lib().ocm_eigh_small_f64(_p(H), m, B, _p(w), _p(U), _stream()), "ocm_eigh_small_f64")
+    return w, U
+
+
+def _orthonormalise(Z):
+    """Batched tall-skinny orthonormalisation [F, p, kb] by Cholesky-QR applied twice (two small Gram products, two
+    kb x kb Cholesky factorisations, two triangular solves: ~0.3 ms where the batched Householder QR takes 2.3 ms at
+    10 x 1050 x 32).  CholQR2 is orthogonal to machine precision while cond(Z)^2 * eps < 1; if a factorisation
+    fails (rank-deficient block) fall back to Householder QR."""
+    torch = _torch()
+    Y = Z
+    for _ in range(2):
+        G = Y.transpose(1, 2) @ Y
+        L, info = torch.linalg.cholesky_ex(G)
+        if bool((info != 0).any()):
+            return torch.linalg.qr(Z)[0]
+        Y = torch.linalg.solve_triangular(L, Y.transpose(1, 2), upper=False).transpose(1, 2)
+    return Y
+
+
+def eig_topk_subspace(Cs, k_need, tol=1e-11, max_iter=60, seed=0):
+    """Leading eigenpairs of a BATCH of symmetric fp64 matrices by block subspace iteration with Rayleigh-Ritz,
+    plus the power sums of the remaining spectrum from traces of the deflated matrices.
+
+    This is what the CV grid needs per fold (loadings up to A_max, eigenvalues up to A_max, theta_1..3 of the rest for
+    the Jackson-Mudholkar / chi2box / ci limits) without a full eigensolve per fold -- ten 1050 x 1050 fp64 `eigh`
+    calls were 90 % of the grid's wall time.  One batched product C Q per iteration; a fold that has not converged
+    after `max_iter` (flat spectrum at A_max) is flagged so the caller can fall back to the full solver.
+
+    Cs [F, p, p].  Returns (w [F, kb] descending Ritz values, X [F, p, kb] Ritz vectors, tails [F, 3] =
+    sums of lambda, lambda^2, lambda^3 beyond the first k_need, converged [F] bool)."""
+    torch = _torch()
+    F, p, _ = Cs.shape
+    kb = min(p, max(k_need + 12, 32))
+    g = torch.Generator(device=Cs.device)
+    g.manual_seed(seed)
+    Q = torch.linalg.qr(torch.randn((F, p, kb), generator=g, dtype=torch.float64, device=Cs.device))[0]
+    conv = torch.zeros(F, dtype=torch.bool, device=Cs.device)
+    w = X = None
+    for it in range(max_iter):
+        Z = Cs @ Q
+        if it % 3 != 2 and it != max_iter - 1:          # two plain power steps per Rayleigh-Ritz step
+            Q = _orthonormalise(Z)
+            continue
+        H = Q.transpose(1, 2) @ Z
+        if kb <= 64:
+            w, U = eigh_small(H)                       # hand-written batched Jacobi (descending)
+        else:
+            w, U = torch.linalg.eigh(0.5 * (H + H.transpose(1, 2)))
+            w, U = w.flip(-1), U.flip(-1)
+        ZU = Z @ U
+        X = Q @ U
+        res = (ZU - X * w.unsqueeze(1)).norm(dim=1)                          # [F, kb] residual norms |C x - w x|
+        conv = res[:, :k_need].max(dim=1).values <= tol * w[:, 0]
+        if bool(conv.all()):
+            break
+        Q = _orthonormalise(ZU)
+    Xk = X[:, :, :k_need]
+    R = Cs - (Xk * w[:, :k_need].unsqueeze(1)) @ Xk.transpose(1, 2)          # deflated: no cancellation in the traces
+    t1 = R.diagonal(dim1=1, dim2=2).sum(-1)
+    t2 = (R * R).sum(dim=(1, 2))
+    t3 = ((R @ R) * R).sum(dim=(1, 2))
+    return w, X, torch.stack([t1, t2, t3], dim=1), conv
+
+
 @dataclass
 class PCAModel:
     """Device-resident PCA of one class: everything predict needs, plus what the reference
@@ -205,6 +278,32 @@ class PCAModel:
     def arrays32(self):
         torch = _torch()
         return self.mean.to(torch.float32), self.P.to(torch.float32).contiguous()
+
+
+def fit_pca_folds(X, row_sets, k) -> list:
+    """PCA models of several row subsets of the same matrix (CV folds): one Gram per subset through its gather
+    index, ONE batched partial eigensolve for all of them (eig_topk_subspace), full solver only for a subset that
+    did not converge.  The returned models carry a `limits.Spectrum` (k leading eigenvalues + tail power sums)
+    instead of the full eigenvalue array."""
+    from .limits import Spectrum
+    torch = _torch()
+    covs, means, ns = [], [], []
+    for idx in row_sets:
+        Cm, mean, n = covariance(X, idx)
+        covs.append(Cm); means.append(mean); ns.append(n)
+    Cs = torch.stack(covs)
+    w, V, tails, conv = eig_topk_subspace(Cs, k)
+    w_h, tails_h, conv_h = w[:, :k].cpu().numpy(), tails.cpu().numpy(), conv.cpu().numpy()
+    models = []
+    for f in range(len(row_sets)):
+        if not conv_h[f]:
+            models.append(fit_pca(X, row_sets[f], k))
+            continue
+        P = V[f, :, :k].transpose(0, 1).contiguous()
+        sign_normalise_(P)
+        lam = np.maximum(w_h[f], 0.0)
+        models.append(PCAModel(mean=means[f], P=P, eigs_all=Spectrum(lam, np.maximum(tails_h[f], 0.0)), n_samples=ns[f]))
+    return models
 
 
 def fit_pca(X, row_idx=None, k=2, group=None) -> PCAModel:

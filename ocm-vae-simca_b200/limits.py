@@ -51,8 +51,29 @@ class Limits:
         return 1.0 / self.T2_limit, 1.0 / self.Q_limit
 
 
+class Spectrum:
+    """Eigenvalue spectrum known as its k leading values plus the power sums of everything beyond them
+    (what a partial eigensolve + traces of the deflated covariance give: engine.eig_topk_subspace)."""
+
+    def __init__(self, top, tail):
+        self.top = np.asarray(top, dtype=np.float64)
+        self.tail = tuple(float(t) for t in tail)       # (sum, sum of squares, sum of cubes) of lambda_{k+1..}
+
+    def __getitem__(self, sl):
+        return self.top[sl]
+
+    def __len__(self):
+        return len(self.top)
+
+
 def tail_moments(eigs_all, A):
     """theta_i = sum_{k>A} lambda_k^i, i=1..3 (SIMCA.py:189-191)."""
+    if isinstance(eigs_all, Spectrum):
+        if A > len(eigs_all.top):
+            raise ValueError("partial spectrum shorter than n_components")
+        rest = eigs_all.top[A:]
+        t1, t2, t3 = eigs_all.tail
+        return float(t1 + rest.sum()), float(t2 + (rest ** 2).sum()), float(t3 + (rest ** 3).sum())
     tail = np.asarray(eigs_all, dtype=np.float64)[A:]
     return float(tail.sum()), float((tail ** 2).sum()), float((tail ** 3).sum())
 

@@ -97,6 +97,7 @@ SIGNATURES = {
     "ocm_gram_f64acc_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ocm_cov_from_parts_f64": (C.c_int, [_vp, _vp, C.POINTER(_i64), C.POINTER(C.c_double), _i32, _i32,
                                          _vp, _vp, _vp, _vp, _vp]),
+    "ocm_eigh_small_f64": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "ocm_simca_score_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                       _vp, _vp, _vp, _vp, _vp]),
     "ocm_simca_score_simt_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),

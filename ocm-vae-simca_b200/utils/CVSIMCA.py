@@ -108,14 +108,17 @@ class _FoldModels:
     def __init__(self, Xd, y, splits, cls, A_max, need_train_scores):
         torch = engine._torch()
         self.folds = []
+        row_sets = []
         for tr, te in splits:
-            tr = np.asarray(tr); te = np.asarray(te)
+            tr = np.asarray(tr)
             rows = tr[y[tr] == cls]
-            idx = engine.index_tensor(rows, Xd.device)
-            n = int(rows.size)
-            if A_max > min(n - 1, Xd.shape[1]):
-                raise ValueError(f"n_components={A_max} too large for a training fold of {n} rows")
-            pca = engine.fit_pca(Xd, idx, A_max)
+            if A_max > min(int(rows.size) - 1, Xd.shape[1]):
+                raise ValueError(f"n_components={A_max} too large for a training fold of {int(rows.size)} rows")
+            row_sets.append(engine.index_tensor(rows, Xd.device))
+        pcas = engine.fit_pca_folds(Xd, row_sets, A_max)       # one batched partial eigensolve for all folds
+        for (tr, te), idx, pca in zip(splits, row_sets, pcas):
+            te = np.asarray(te)
+            n = int(idx.numel())
             inv_eig = torch.as_tensor(1.0 / pca.eigs_all[:A_max], device=Xd.device)
             te_idx = engine.index_tensor(te, Xd.device)
             f = dict(pca=pca, n=n, te=te, te_idx=te_idx, Xte=Xd.index_select(0, te_idx), inv_eig=inv_eig,

@@ -193,6 +193,21 @@ def test_gram_kernels_match_numpy(torch):
             np.testing.assert_allclose(np.triu(G2.cpu().numpy()), 2 * ref, rtol=1e-11, atol=1e-10 * np.abs(ref).max())
 
 
+def test_small_jacobi_eigensolver(torch):
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda")
+    for m in (1, 2, 7, 32, 45, 64):
+        M = rng.normal(size=(6, m, m)); H = M @ M.transpose(0, 2, 1) * np.logspace(0, -6, 6)[:, None, None]
+        H[1] = np.diag(np.arange(m, 0, -1.0))            # already diagonal
+        w, U = engine.eigh_small(torch.as_tensor(H, device=dev))
+        w, U = w.cpu().numpy(), U.cpu().numpy()
+        for b in range(6):
+            ref = np.linalg.eigvalsh(H[b])[::-1]
+            np.testing.assert_allclose(w[b], ref, rtol=1e-10, atol=1e-13 * abs(ref[0]))
+            np.testing.assert_allclose(U[b].T @ U[b], np.eye(m), atol=1e-12)
+            np.testing.assert_allclose(H[b] @ U[b], U[b] * w[b], atol=1e-11 * abs(ref[0]))
+
+
 def test_preprocess_kernels(torch):
     rng = np.random.default_rng(0)
     for p in (700, 1024, 1050):
