@@ -334,6 +334,49 @@ def test_tensor_core_kernel_matches_oracle(torch):
         assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
 
 
+def test_nonfinite_rows_are_rejected_and_isolated(torch):
+    """The reference's drivers drop NaN / inf spectra before SIMCA (simca_nuts.py:55-66); if one slips through, numpy
+    gives NaN distances and `NaN < limit` is False.  Every kernel must do the same and must not let a bad row touch
+    its neighbours (tensor-core tiles share MMAs across 128 rows)."""
+    dev = torch.device("cuda")
+    n, p, A = 40_000, 1024, 10
+    X = synth.make_spectra_device(n, p, dev, seed=77)
+    pca = engine.fit_pca(X[:3000].contiguous(), None, A)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+    bad = [0, 127, 128, 4097, n - 1]
+    Xb = X.clone()
+    Xb[bad[0], 5] = float("nan"); Xb[bad[1], 1023] = float("inf"); Xb[bad[2], 0] = float("-inf")
+    Xb[bad[3], 512] = float("nan"); Xb[bad[4], 700] = float("nan")
+    clean = engine.score(X, pca.mean, pca.P, Sinv, ct=0.05, cq=50.0)            # dispatcher -> tcgen05 kernel
+    for kw in ({}, {"force_simt": True}):
+        T2, Q, acc = engine.score(Xb, pca.mean, pca.P, Sinv, ct=0.05, cq=50.0, **kw)
+        ok = torch.ones(n, dtype=torch.bool, device=dev); ok[bad] = False
+        assert not torch.isfinite(Q[bad]).any() and int(acc[bad].sum()) == 0
+        assert torch.isfinite(T2[ok]).all() and torch.isfinite(Q[ok]).all()
+        if not kw:
+            assert torch.equal(T2[ok], clean[0][ok]) and torch.equal(Q[ok], clean[1][ok]) and torch.equal(acc[ok], clean[2][ok])
+    import os
+    prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
+    mu32, P32 = pca.arrays32(); S32 = Sinv.float().contiguous()
+    T2 = torch.empty(n, device=dev); Q = torch.empty(n, device=dev); acc = torch.empty(n, dtype=torch.uint8, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    native.check(native.lib().ocm_simca_score_rowteam_f32(vp(Xb), n, p, p, vp(mu32), vp(P32), vp(S32), C.byref(prm), vp(T2), vp(Q),
+                                                          vp(acc), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert not torch.isfinite(Q[bad]).any() and int(acc[bad].sum()) == 0 and torch.isfinite(Q[ok]).all()
+
+
+def test_empty_inputs(torch):
+    X, y = synth.make_class_dataset(60, 20, 64, seed=2)
+    m = SIMCA(n_components=3, model_class=0, verbose=False).fit(X, y)
+    assert m.predict(np.zeros((0, 64))).shape == (0, 1)
+    T2, T2r, Q, Qr = m.transform(np.zeros((0, 64)))
+    assert T2.shape == (0,) and Q.shape == (0,)
+    dev = torch.device("cuda")
+    d2, q = engine.latent_score(z=torch.zeros((0, 4), device=dev), m=torch.zeros(4, device=dev), Sinv=torch.eye(4, device=dev),
+                                x=torch.zeros((0, 8), device=dev), xrec=torch.zeros((0, 8), device=dev))
+    assert d2.shape == (0,) and q.shape == (0,)
+
+
 def test_host_buffer_api(torch):
     X = synth.make_spectra(5000, 1024, seed=12).astype(np.float32)
     ref = so.fit_one_class(X[:2000].astype(np.float64), 10)
