@@ -57,6 +57,15 @@ int ocm_preprocess_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_
                        const float* mu, const float* sigma, float eps,
                        float* Y, int64_t ldy, void* stream);
 
+/* ---- f1: Savitzky-Golay filter, optionally after row SNV (simca_nuts.py:48-52, utils/data_utils.py:57-59:
+ * scipy.signal.savgol_filter(window_length=5, polyorder=2, deriv=1, mode='interp')).  h_coef [window] (HOST) are the
+ * interior taps g, y[i] = sum_d g[d] x[i + d - window/2]; edge_l / edge_r [window/2][window] (device) map the first /
+ * last `window` samples to the window/2 outputs at each end (the polynomial-fit edges of mode 'interp').
+ * Out of place only. */
+int ocm_savgol_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_t snv, float eps,
+                   const float* h_coef, int32_t window, const float* edge_l, const float* edge_r,
+                   float* Y, int64_t ldy, void* stream);
+
 /* ---- a2 / a4: column moments of selected rows -----------------------------------------
  * colsum[j] += sum_r (x[r][j] - shift[j]),  colsumsq[j] += sum_r (x[r][j] - shift[j])^2 in fp64.
  * row_idx (int64, may be NULL = rows 0..n-1) gathers rows; shift / colsumsq may be NULL.

@@ -139,3 +139,179 @@ extern "C" int ocm_preprocess_f32(const float* X, int64_t n, int32_t p, int64_t 
         preprocess_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(X, n, p, ldx, mode, mu, sigma, eps, Y, ldy);
     return check_launch("preprocess_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Savitzky-Golay filter (optionally after SNV) -- SURVEY.md §8(f) f1: the step between SNV and SIMCA in every
+// reference driver (simca_nuts.py:52, utils/data_utils.py:59: window 5, polyorder 2, deriv 1, scipy mode 'interp').
+// A p-point FIR once the row is on chip: one warp per row, row staged in shared memory (after SNV if requested),
+// interior points y[i] = sum_d g[d] x[i+d-h], the h points at each end from the polynomial fitted to the first /
+// last `window` samples, given as two small matrices computed on the host from the same scipy routine.
+// HBM-bound: 8*p bytes per spectrum.
+namespace ocm {
+
+constexpr int SG_MAXW = 33;
+
+struct SavgolArgs {
+    int window, half;
+    float g[SG_MAXW];
+};
+
+__global__ void __launch_bounds__(128)
+savgol_kernel(const float* __restrict__ X, int64_t n, int p, int64_t ldx, int snv, float eps, SavgolArgs sg,
+              const float* __restrict__ edge_l, const float* __restrict__ edge_r, float* __restrict__ Y, int64_t ldy) {
+    extern __shared__ float s_rows[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* row = s_rows + (size_t)w * p;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int h = sg.half, win = sg.window;
+    for (int64_t r = wid; r < n; r += nw) {
+        const float* x = X + r * ldx;
+        float s = 0.f;
+        for (int j = lane; j < p; j += 32) { const float v = x[j]; row[j] = v; s += v; }
+        if (snv) {
+            const float m = warp_sum(s) / (float)p;
+            float ss = 0.f;
+            for (int j = lane; j < p; j += 32) { const float d = row[j] - m; ss = fmaf(d, d, ss); }
+            const float inv = 1.f / (sqrtf(warp_sum(ss) / (float)p) + eps);
+            for (int j = lane; j < p; j += 32) row[j] = (row[j] - m) * inv;
+        }
+        __syncwarp();
+        float* y = Y + r * ldy;
+        for (int j = lane; j < p; j += 32) {
+            float acc = 0.f;
+            if (j >= h && j < p - h) {
+#pragma unroll 5
+                for (int d = 0; d < win; ++d) acc = fmaf(sg.g[d], row[j + d - h], acc);
+            } else if (j < h) {
+                for (int d = 0; d < win; ++d) acc = fmaf(edge_l[j * win + d], row[d], acc);
+            } else {
+                const int e = j - (p - h);
+                for (int d = 0; d < win; ++d) acc = fmaf(edge_r[e * win + d], row[p - win + d], acc);
+            }
+            y[j] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// Vector path: 128-bit loads / stores, window length known at compile time so the taps sit in the constant bank and
+// the window lives in registers; SNV is applied as (x - m) on the way into the window and * inv on the way out, so the
+// staged row is written once.  Per 4 outputs: 1 STS.128 + 1 LDS.128 (variance pass) + (1 + 2*ceil(h/4)) LDS.128.
+template <int W>
+__global__ void __launch_bounds__(128)
+savgol_vec_kernel(const float* __restrict__ X, int64_t n, int p, int64_t ldx, int snv, float eps, SavgolArgs sg,
+                  const float* __restrict__ edge_l, const float* __restrict__ edge_r, float* __restrict__ Y, int64_t ldy) {
+    constexpr int H = W / 2, HP4 = (H + 3) / 4, HP = HP4 * 4, NV4 = 1 + 2 * HP4;
+    extern __shared__ float4 s_rows4[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nch = p >> 2;
+    float4* row4 = s_rows4 + (size_t)w * nch;
+    const float* row = reinterpret_cast<const float*>(row4);
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = wid; r < n; r += nw) {
+        const float* x = X + r * ldx;
+        float s = 0.f;
+        for (int c = lane; c < nch; c += 32) {
+            const float4 v = ldg_stream4(x + 4 * c);
+            row4[c] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+        float m = 0.f, inv = 1.f;
+        if (snv) {
+            m = warp_sum(s) / (float)p;
+            float ss = 0.f;
+            for (int c = lane; c < nch; c += 32) {
+                const float4 v = row4[c];
+                const float a = v.x - m, b = v.y - m, cc = v.z - m, d = v.w - m;
+                ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(cc, cc, ss); ss = fmaf(d, d, ss);
+            }
+            inv = 1.f / (sqrtf(warp_sum(ss) / (float)p) + eps);
+        }
+        __syncwarp();
+        float* y = Y + r * ldy;
+        for (int c = lane; c < nch; c += 32) {
+            float v[4 * NV4];
+#pragma unroll
+            for (int k = 0; k < NV4; ++k) {
+                const int cc = c - HP4 + k;
+                float4 t = make_float4(m, m, m, m);
+                if (cc >= 0 && cc < nch) t = row4[cc];
+                v[4 * k + 0] = t.x - m; v[4 * k + 1] = t.y - m; v[4 * k + 2] = t.z - m; v[4 * k + 3] = t.w - m;
+            }
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < W; ++d) acc = fmaf(sg.g[d], v[HP - H + q + d], acc);
+                o[q] = acc;
+            }
+            const int j0 = 4 * c;
+            if (j0 < H || j0 + 3 >= p - H) {              // the polynomial-fit ends (mode 'interp')
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + q;
+                    if (j < H) {
+                        float acc = 0.f;
+                        for (int d = 0; d < W; ++d) acc = fmaf(edge_l[j * W + d], row[d] - m, acc);
+                        o[q] = acc;
+                    } else if (j >= p - H) {
+                        float acc = 0.f;
+                        for (int d = 0; d < W; ++d) acc = fmaf(edge_r[(j - (p - H)) * W + d], row[p - W + d] - m, acc);
+                        o[q] = acc;
+                    }
+                }
+            }
+            __stcs(reinterpret_cast<float4*>(y) + c, make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv));
+        }
+        __syncwarp();
+    }
+}
+
+template <int W>
+static cudaError_t launch_savgol_vec(unsigned blocks, size_t smem, cudaStream_t st, const float* X, int64_t n, int p, int64_t ldx,
+                                     int snv, float eps, const SavgolArgs& sg, const float* el, const float* er, float* Y, int64_t ldy) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(savgol_vec_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    savgol_vec_kernel<W><<<blocks, 128, smem, st>>>(X, n, p, ldx, snv, eps, sg, el, er, Y, ldy);
+    return cudaSuccess;
+}
+
+}  // namespace ocm
+
+extern "C" int ocm_savgol_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_t snv, float eps,
+                              const float* h_coef, int32_t window, const float* edge_l, const float* edge_r,
+                              float* Y, int64_t ldy, void* stream) {
+    using namespace ocm;
+    if (n == 0) return 0;
+    OCM_REQUIRE(X && Y && h_coef && edge_l && edge_r && n > 0 && p > 0 && ldx >= p && ldy >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    OCM_REQUIRE(window >= 3 && (window & 1) && window <= SG_MAXW && window <= p, OCM_ELIMIT, "window must be odd, 3..33 and <= p");
+    OCM_REQUIRE(X != Y, OCM_EINVAL, "in-place filtering is not supported");
+    OCM_REQUIRE((size_t)p * 4 * 4 <= 200 * 1024, OCM_ELIMIT, "row too long for the shared-memory stage (p <= 12800)");
+    SavgolArgs sg;
+    sg.window = window; sg.half = window / 2;
+    for (int i = 0; i < window; ++i) sg.g[i] = h_coef[i];
+    const size_t smem = (size_t)4 * p * sizeof(float);
+    if (smem > 48 * 1024) OCM_CUDA(cudaFuncSetAttribute(savgol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (n + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const bool vec = p % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)Y & 15) == 0;
+    if (vec && window >= 5 && window <= 15) {
+        cudaError_t e = cudaSuccess;
+        const cudaStream_t st = (cudaStream_t)stream;
+        switch (window) {
+#define OCM_SG_CASE(W_) case W_: e = launch_savgol_vec<W_>((unsigned)blocks, smem, st, X, n, p, ldx, snv, eps, sg, edge_l, edge_r, Y, ldy); break;
+            OCM_SG_CASE(5) OCM_SG_CASE(7) OCM_SG_CASE(9) OCM_SG_CASE(11) OCM_SG_CASE(13) OCM_SG_CASE(15)
+#undef OCM_SG_CASE
+        }
+        OCM_CUDA(e);
+        return check_launch("savgol_vec_kernel");
+    }
+    savgol_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(X, n, p, ldx, snv, eps, sg, edge_l, edge_r, Y, ldy);
+    return check_launch("savgol_kernel");
+}

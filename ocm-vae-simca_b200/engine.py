@@ -87,6 +87,59 @@ def snv(X, eps=1e-8):
     return preprocess(X, "snv", eps=eps)
 
 
+_SG_CACHE = {}
+
+
+def _savgol_tables(window, polyorder, deriv, delta):
+    """Interior taps and the two edge matrices of scipy's savgol_filter(mode='interp'), obtained by pushing unit
+    impulses through scipy itself, so the device filter is the same linear map by construction."""
+    key = (window, polyorder, deriv, float(delta))
+    if key not in _SG_CACHE:
+        from scipy.signal import savgol_filter
+        h = window // 2
+        L = 3 * window
+        resp = savgol_filter(np.eye(L), window, polyorder, deriv=deriv, delta=delta, axis=1)   # row j: response to impulse at j
+        c = L // 2
+        g = np.array([resp[c + d - h, c] for d in range(window)])                 # y[c] = sum_d g[d] x[c + d - h]
+        edge_l = resp[:window, :h].T.copy()                                       # y[i<h] from x[0:window]
+        edge_r = resp[L - window:, L - h:].T.copy()                               # y[L-h+i] from x[L-window:L]
+        _SG_CACHE[key] = (g.astype(np.float32), edge_l.astype(np.float32), edge_r.astype(np.float32))
+    return _SG_CACHE[key]
+
+
+def savgol(X, window_length=5, polyorder=2, deriv=1, delta=1.0, snv=False, snv_eps=1e-8, out=None):
+    """[SNV +] Savitzky-Golay filter of fp32 device rows in one pass (ocm_savgol_f32)."""
+    torch = _torch()
+    X = to_device(X, dtype=torch.float32)
+    if out is None:
+        out = torch.empty_like(X)
+    g, el, er = _savgol_tables(int(window_length), int(polyorder), int(deriv), delta)
+    el_d = torch.as_tensor(el, device=X.device).contiguous()
+    er_d = torch.as_tensor(er, device=X.device).contiguous()
+    rc = native.lib().ocm_savgol_f32(_p(X), X.shape[0], X.shape[1], X.stride(0), int(bool(snv)), float(snv_eps),
+                                     g.ctypes.data_as(C.c_void_p), int(window_length), _p(el_d), _p(er_d), _p(out),
+                                     out.stride(0), _stream())
+    native.check(rc, "ocm_savgol_f32")
+    return out
+
+
+def mahalanobis_outlier_mask(X, n_components=10, percentile=95.0):
+    """PCA score-space Mahalanobis outlier filter (simca_nuts.py:127-147, utils/data_utils.py:65-80):
+    fit PCA(n_components) on X, d_i = sqrt(t_i^T cov(T)^-1 t_i) (= sqrt of the Hotelling T2 the scoring kernel returns,
+    because cov(T) = diag(lambda)), keep rows with d_i <= percentile(d).  Returns (keep mask [n] bool on the device,
+    distances [n] fp32, threshold)."""
+    torch = _torch()
+    X = to_device(X)
+    n, p = X.shape
+    k = min(int(n_components), p, max(1, n - 1))
+    pca = fit_pca(X, None, k)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:k], device=X.device))
+    T2, _, _ = score(X, pca.mean, pca.P, Sinv)
+    d = torch.sqrt(T2.clamp_min(0).double())
+    thr = torch.quantile(d, float(percentile) / 100.0, interpolation="linear")
+    return d <= thr, d, float(thr.item())
+
+
 # ------------------------------------------------------------------------------------------
 # PCA fit: moments -> covariance -> eigh
 # ------------------------------------------------------------------------------------------

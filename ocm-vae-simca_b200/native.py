@@ -91,6 +91,7 @@ SIGNATURES = {
     "ocm_last_error": (C.c_char_p, []),
     "ocm_launch_count": (C.c_uint64, []),
     "ocm_preprocess_f32": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),
+    "ocm_savgol_f32": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "ocm_colstats_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ocm_colstats_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ocm_gram_f64acc_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -75,6 +75,30 @@ def make_class_dataset(n_target: int, n_other: int, p: int, seed: int = 0,
     return np.ascontiguousarray(X, dtype=dtype), y
 
 
+def make_object_dataset(nuts=("almond", "hazelnut", "walnut"), n_objects=8, rows=(30, 60), p=120, seed=0,
+                        n_bad=3, n_gross=4):
+    """Acquisition-shaped input of `object_aware_splits` (/root/reference/utils/data_utils.py:12): per nut type a list
+    of objects, each {'spectral_data': float32 [rows_i, p]} -- with a few NaN / inf rows and a few gross outliers
+    planted so that both screens have something to remove.  Each object gets its own offset so that objects differ."""
+    rng = np.random.default_rng(seed)
+    data = {}
+    for k, nut in enumerate(nuts):
+        objs = []
+        for o in range(n_objects):
+            r = int(rng.integers(rows[0], rows[1] + 1))
+            X = make_spectra(r, p, seed=seed * 1000 + k * 100 + o, shift=0.02 * k).astype(np.float32)
+            X += np.float32(0.01 * rng.standard_normal())
+            objs.append({"spectral_data": X})
+        for _ in range(n_gross):
+            o = int(rng.integers(n_objects)); X = objs[o]["spectral_data"]
+            X[int(rng.integers(X.shape[0]))] += (0.2 * rng.standard_normal(p)).astype(np.float32)
+        for b in range(n_bad):
+            o = int(rng.integers(n_objects)); X = objs[o]["spectral_data"]
+            X[int(rng.integers(X.shape[0])), int(rng.integers(p))] = np.nan if b % 2 == 0 else np.inf
+        data[nut] = objs
+    return data
+
+
 def make_spectra_device(n: int, p: int, device, seed: int = 0, shift: float = 0.0,
                         decay: float = 0.8, noise: float = 1e-3, chunk: int = 1 << 18,
                         out=None):

@@ -199,6 +199,32 @@ def golden_vae(ref_vae):
                         L=L, d=d, **out)
 
 
+def golden_splits(ref, synth):
+    """object_aware_splits of the live reference on a small acquisition-shaped set (3 nut types x 8 objects, p=120;
+    every per-nut matrix has max(shape) <= 500 so the reference's PCA(svd_solver='auto') is the exact 'full' solver and
+    the fixture is deterministic)."""
+    kw = dict(nuts=("almond", "hazelnut", "walnut"), n_objects=8, rows=(30, 60), p=120, seed=5)
+    data = synth.make_object_dataset(**kw)
+    assert all(sum(o["spectral_data"].shape[0] for o in v) <= 500 for v in data.values())
+    splits, Xts, yts, Xcal, Xval, Xtin, Xtout = quiet(ref.object_aware_splits, data, list(kw["nuts"]), "almond", 120)
+    np.savez_compressed(os.path.join(GOLD, "object_splits.npz"), seed=5, Xts=Xts, yts=yts, Xcal=Xcal, Xval=Xval,
+                        Xtin=Xtin, Xtout=Xtout,
+                        shapes=np.array([[splits[n][k].shape[0] for k in ("cal", "val", "test")] for n in kw["nuts"]]))
+    # the preprocessing + distance step on its own (data_utils.py:57-77 re-run here line by line with the same
+    # library calls) so that the kernels have a numeric target too
+    from scipy.signal import savgol_filter
+    from sklearn.decomposition import PCA
+    X = np.vstack([o["spectral_data"] for o in data["hazelnut"]])
+    X = X[np.isfinite(X).all(axis=1)]
+    Xp = (X - np.mean(X, axis=1, keepdims=True)) / (np.std(X, axis=1, keepdims=True) + 1e-8)
+    Xp = savgol_filter(Xp, window_length=5, polyorder=2, deriv=1, axis=1)
+    T = PCA(n_components=10).fit_transform(Xp)
+    ci = np.linalg.pinv(np.cov(T, rowvar=False))
+    mahal = np.array([np.sqrt((t - T.mean(0)) @ ci @ (t - T.mean(0)).T) for t in T])
+    np.savez_compressed(os.path.join(GOLD, "snv_savgol_mahal.npz"), X=X, Xp=Xp, mahal=mahal,
+                        thr=np.percentile(mahal, 95))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--c2", action="store_true")
@@ -211,6 +237,7 @@ def main():
     golden_ncomp_sweep(ref, synth)
     golden_cv_small(ref, synth)
     golden_vae(ref_vae)
+    golden_splits(ref, synth)
     if args.c2:
         golden_c2(ref, synth)
     print("fixtures written to", GOLD)

@@ -216,3 +216,70 @@ def cv_grid(X, y, splits, lv_values, model_class=0, class_index=None, refit=True
 def snv(X, eps=1e-8):
     """Row SNV as the drivers apply it.  simca_nuts.py:48-50."""
     return (X - X.mean(axis=1, keepdims=True)) / (X.std(axis=1, keepdims=True) + eps)
+
+
+def snv_savgol(X, window_length=5, polyorder=2, deriv=1):
+    """SNV followed by the Savitzky-Golay derivative of the drivers (simca_nuts.py:48-52, utils/data_utils.py:57-59)."""
+    from scipy.signal import savgol_filter
+    return savgol_filter(snv(X), window_length=window_length, polyorder=polyorder, deriv=deriv, axis=1)
+
+
+def mahalanobis_filter(X, n_components=10, percentile=95, faithful_solver=False):
+    """PCA score-space outlier cut (simca_nuts.py:127-147, utils/data_utils.py:65-80): returns (keep mask, distances, threshold).
+    The reference's PCA(n_components) runs svd_solver='auto', i.e. an UNSEEDED randomized SVD at these shapes (quirk Q1
+    again: its distances move by ~5e-4 from call to call); parity pins the exact decomposition."""
+    T = PCA(n_components=n_components, svd_solver="auto" if faithful_solver else "full").fit_transform(X)
+    diff = T - T.mean(axis=0)
+    cov_inv = np.linalg.pinv(np.cov(T, rowvar=False))
+    d = np.sqrt(np.einsum("ij,jk,ik->i", diff, cov_inv, diff))
+    thr = np.percentile(d, percentile)
+    return d <= thr, d, thr
+
+
+def object_aware_splits(data, nut_types, target_nut, p, cal_frac=0.7, val_frac=0.15, test_frac=0.15,
+                        random_state=42, outlier_percentile=95, use_pca=True, faithful_solver=False):
+    """Restatement of utils/data_utils.py:12-169: per nut type stack the objects, drop non-finite rows (:49-54), drop
+    rows beyond the P-th percentile of the PCA(<=10) score-space Mahalanobis distance of the SNV + SavGol copy
+    (:57-80), send whole objects to cal / val / test with two seeded train_test_split calls (:103-120), then assemble
+    the pooled test set with labels 0 = target / 1 = other (:133-167)."""
+    from sklearn.model_selection import train_test_split
+    empty = lambda: np.empty((0, p), dtype=np.float32)
+    splits = {}
+    for nut in nut_types:
+        objs = [np.asarray(o["spectral_data"], dtype=np.float32) for o in data[nut]]
+        splits[nut] = dict(cal=empty(), val=empty(), test=empty())
+        if not objs:
+            continue
+        X = np.vstack(objs)
+        ids = np.concatenate([np.full(len(o), i, dtype=int) for i, o in enumerate(objs)])
+        ok = np.isfinite(X).all(axis=1)
+        X, ids = X[ok], ids[ok]
+        n = X.shape[0]
+        if use_pca and n > 3:
+            k = min(10, X.shape[1], max(1, n - 1))
+            if n > k:
+                Xp = (X - np.mean(X, axis=1, keepdims=True)) / (np.std(X, axis=1, keepdims=True) + 1e-8)
+                if X.shape[1] >= 5:
+                    from scipy.signal import savgol_filter
+                    Xp = savgol_filter(Xp, window_length=5, polyorder=2, deriv=1, axis=1)
+                keep, _, _ = mahalanobis_filter(Xp, k, outlier_percentile, faithful_solver=faithful_solver)
+                X, ids = X[keep], ids[keep]
+        uniq = [int(i) for i in np.unique(ids)]
+        if not uniq:
+            continue
+        if len(uniq) >= 3:
+            cal, tmp = train_test_split(uniq, test_size=1.0 - cal_frac, random_state=random_state)
+            rel = test_frac / (val_frac + test_frac) if (val_frac + test_frac) > 0 else 0.5
+            val, tst = train_test_split(tmp, test_size=rel, random_state=random_state)
+        else:
+            cal, val, tst = [uniq[0]], [], ([uniq[1]] if len(uniq) == 2 else [])
+        for name, sel in (("cal", cal), ("val", val), ("test", tst)):
+            if sel:
+                splits[nut][name] = np.vstack([X[ids == i] for i in sel])
+    tests = [(nut, splits[nut]["test"]) for nut in nut_types if len(splits[nut]["test"])]
+    Xts = np.vstack([t for _, t in tests]) if tests else empty()
+    yts = (np.concatenate([np.full(len(t), int(nut != target_nut)) for nut, t in tests]) if tests
+           else np.array([], dtype=int))
+    out = [t for nut, t in tests if nut != target_nut]
+    tg = splits[target_nut]
+    return splits, Xts, yts, tg["cal"], tg["val"], tg["test"], (np.vstack(out) if out else empty())

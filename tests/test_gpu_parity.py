@@ -223,6 +223,56 @@ def test_preprocess_kernels(torch):
     assert engine.snv(np.zeros((0, 16), np.float32)).shape == (0, 16)
 
 
+def test_savgol_and_outlier_filter(torch):
+    """§8(f) f1 / f2: SNV + Savitzky-Golay derivative in one pass, PCA-Mahalanobis outlier cut."""
+    rng = np.random.default_rng(4)
+    for p, win in ((700, 5), (1050, 15), (1024, 15), (256, 9), (128, 13), (16, 15), (64, 5), (33, 33)):
+        X = synth.make_spectra(123, p, seed=p).astype(np.float32)
+        ref = so.snv_savgol(X.astype(np.float64), window_length=win)
+        got = engine.savgol(X, window_length=win, polyorder=2, deriv=1, snv=True).cpu().numpy()
+        scale = np.abs(ref).max()
+        np.testing.assert_allclose(got, ref, rtol=0, atol=3e-5 * scale, err_msg=f"p={p} win={win}")
+        from scipy.signal import savgol_filter
+        ref2 = savgol_filter(X.astype(np.float64), win, 3, deriv=0, axis=1)
+        got2 = engine.savgol(X, window_length=win, polyorder=3, deriv=0).cpu().numpy()
+        np.testing.assert_allclose(got2, ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
+    X = so.snv_savgol(synth.make_spectra(800, 300, seed=9))
+    X[::97] += rng.normal(0, 0.05, (len(X[::97]), 300))          # a few gross outliers
+    keep_r, d_r, thr_r = so.mahalanobis_filter(X, 10, 95)
+    keep, d, thr = engine.mahalanobis_outlier_mask(X, 10, 95.0)
+    np.testing.assert_allclose(d.cpu().numpy(), d_r, rtol=2e-5)
+    np.testing.assert_allclose(thr, thr_r, rtol=2e-5)
+    assert (keep.cpu().numpy() != keep_r).sum() <= 1
+
+
+def test_object_aware_splits_against_reference_golden(torch, golden_dir):
+    """§8(f): the drop-in `object_aware_splits` returns the reference's arrays bit for bit; its device preprocessing
+    and distances match the reference's to fp32 accuracy."""
+    from ocm_vae_simca_b200.utils import object_aware_splits
+    g = load(golden_dir, "object_splits.npz")
+    nuts = ["almond", "hazelnut", "walnut"]
+    data = synth.make_object_dataset(seed=int(g["seed"]))
+    splits, Xts, yts, Xcal, Xval, Xtin, Xtout = object_aware_splits(data, nuts, "almond", 120)
+    for got, key in ((Xts, "Xts"), (yts, "yts"), (Xcal, "Xcal"), (Xval, "Xval"), (Xtin, "Xtin"), (Xtout, "Xtout")):
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+    assert [[splits[n][k].shape[0] for k in ("cal", "val", "test")] for n in nuts] == g["shapes"].tolist()
+    h = load(golden_dir, "snv_savgol_mahal.npz")
+    Xp = engine.savgol(h["X"], 5, 2, 1, snv=True)
+    np.testing.assert_allclose(Xp.cpu().numpy(), h["Xp"], rtol=0, atol=3e-5 * np.abs(h["Xp"]).max())
+    _, d, thr = engine.mahalanobis_outlier_mask(Xp, 10, 95.0)
+    np.testing.assert_allclose(d.cpu().numpy(), h["mahal"], rtol=2e-4)      # fp32 SNV + SavGol in front of the PCA
+    np.testing.assert_allclose(thr, h["thr"], rtol=2e-4)
+    tiny = {"a": [], "b": data["almond"][:1], "c": data["walnut"][:2]}
+    want = so.object_aware_splits(tiny, ["a", "b", "c"], "b", 120)
+    got = object_aware_splits(tiny, ["a", "b", "c"], "b", 120)
+    for a, b in zip(got[1:], want[1:]):
+        assert np.array_equal(a, b)
+    got = object_aware_splits(data, nuts, "walnut", 120, use_pca=False)
+    want = so.object_aware_splits(data, nuts, "walnut", 120, use_pca=False)
+    for a, b in zip(got[1:], want[1:]):
+        assert np.array_equal(a, b)
+
+
 def test_fused_snv_scoring(torch):
     Xraw = synth.make_spectra(300, 512, seed=8)
     Xs = so.snv(Xraw)

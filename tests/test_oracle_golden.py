@@ -98,6 +98,28 @@ def test_c2_single_column(golden_dir):
         assert np.array_equal(so.predict(m, X[te]).astype(np.uint8), pooled[col][te])
 
 
+def test_object_aware_splits(golden_dir):
+    """Oracle restatement of object_aware_splits and of its SNV + SavGol + Mahalanobis step vs the live reference."""
+    g = load(golden_dir, "object_splits.npz")
+    data = synth.make_object_dataset(seed=int(g["seed"]))
+    nuts = ["almond", "hazelnut", "walnut"]
+    splits, Xts, yts, Xcal, Xval, Xtin, Xtout = so.object_aware_splits(data, nuts, "almond", 120)
+    for got, key in ((Xts, "Xts"), (yts, "yts"), (Xcal, "Xcal"), (Xval, "Xval"), (Xtin, "Xtin"), (Xtout, "Xtout")):
+        assert np.array_equal(got, g[key]), key
+    assert [[splits[n][k].shape[0] for k in ("cal", "val", "test")] for n in nuts] == g["shapes"].tolist()
+    h = load(golden_dir, "snv_savgol_mahal.npz")
+    Xp = so.snv_savgol(h["X"])
+    np.testing.assert_allclose(Xp, h["Xp"], rtol=0, atol=1e-12)
+    keep, d, thr = so.mahalanobis_filter(Xp, 10, 95)
+    np.testing.assert_allclose(d, h["mahal"], rtol=1e-9)
+    np.testing.assert_allclose(thr, h["thr"], rtol=1e-9)
+    # degenerate inputs the reference handles: empty nut, one and two objects
+    tiny = {"a": [], "b": data["almond"][:1], "c": data["walnut"][:2]}
+    sp, Xts, yts, Xcal, *_ = so.object_aware_splits(tiny, ["a", "b", "c"], "b", 120)
+    assert sp["a"]["cal"].shape == (0, 120) and sp["b"]["test"].shape[0] == 0 and sp["c"]["val"].shape[0] == 0
+    assert set(yts.tolist()) == {1} and Xcal.shape[0] > 0
+
+
 def test_conformity_matches_counts():
     y = np.array([0, 0, 1, 1, 0, 1]); p = np.array([1, 0, 0, 1, 1, 0.0])
     m = so.conformity(y, p, 0)
