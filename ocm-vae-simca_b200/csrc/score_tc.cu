@@ -107,7 +107,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // bounded wait: a protocol bug must not hang the GPU; it raises a flag the host can read.
-// (A/B-tested on the B200: a leaner polling loop and try_wait suspend hints were both ~6 % SLOWER than this one.)
+// (A/B-tested on the B200, twice: a leaner polling loop -- PTX loop around try_wait, 5 instructions per round -- is
+// 10 % SLOWER end to end than this one, try_wait suspend hints 6 % slower, and a __nanosleep back-off of 20..200 ns
+// makes no difference.  The loop stays as it is.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -115,6 +117,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if ((spins & 0x3FFFu) == 0 && *reinterpret_cast<volatile unsigned int*>(&g_tc_timeout)) break;  // someone already gave up
         if (spins > (1u << 20)) { atomicExch(&g_tc_timeout, 1u); break; }
     }
+}
+__device__ __forceinline__ ulonglong2 lds128(uint32_t addr) {
+    ulonglong2 r;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(addr) : "memory");
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -263,10 +270,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     constexpr int W_TMA = NCONV / 32, W_MMA = NCONV / 32 + 1;   // MMA warps: W_MMA .. W_MMA + NMMAW - 1
     static_assert(NMMAW == 2, "MMA warp j owns residual buffer j");
     const int ns = a.ns, nc = a.ns / SUBS;                      // stages per pass, residual chunks per tile
-    // mbarrier phase of the u-th use of a buffer is u & 1.  Use counts: A buffer b, tile k, stage `chunk`:
-    // k*ns/2 + chunk/2 ; residual buffer b, tile k, chunk c2: k*ceil-or-floor(nc/2) + c2/2.
-    auto a_use = [&](int64_t k, int chunk) { return (uint32_t)((k * (ns >> 1) + (chunk >> 1)) & 1); };
-    auto d_use = [&](int64_t k, int c2) { return (uint32_t)((k * ((nc + 1 - (c2 & 1)) >> 1) + (c2 >> 1)) & 1); };
+    // mbarrier phase of the u-th use of a buffer is u & 1; every role keeps the phase of its next use as a running bit
+    // (A buffers are used in pairs, one stage each; residual buffer b serves chunks b, b+2, ...).
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
@@ -337,16 +342,55 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 
         float t2_row = 0.f, q_acc = 0.f;
 
-        // residual chunk c2 back from TMEM: my lane, my 2 x 16 columns (buffer b = c2 & 1, (c2/2)-th use in the tile)
-        auto read_d2 = [&](int64_t k, int c2) {
-            const int b = c2 & 1;
-            mbar_wait(BAR(B_DREADY + b), d_use(k, c2));
+        // All per-stage state is kept incrementally in 32-bit registers (shared-space addresses, phase bits): the first
+        // version recomputed slots, barrier addresses and use counts (64-bit) every stage, ~75 scalar instructions per
+        // 16 elements, and those sit on the same ALU pipe as the split masks and packs (ncu: ALU pipe 55 % busy,
+        // issue-limited converters).
+        const uint32_t ring0 = sb + (uint32_t)SM_OFF_RING + my_off;
+        uint32_t xo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xo[i] = (uint32_t)(((c_base + i) ^ rsw) << 4);
+        const uint32_t mu0 = sb + (uint32_t)SM_OFF_MU + 4u * (uint32_t)(QCOLS * qd);
+        const uint32_t bar_full0 = BAR(B_FULL), bar_empty0 = BAR(B_EMPTY);
+        uint32_t st = ring0, bar_full = bar_full0, bar_empty = bar_empty0, ring_phase = 0;
+        int slot = 0;
+        uint32_t aph = 0;      // parity of the current use of the A buffers (they advance in pairs)
+        uint32_t dph = 0;      // bit b: parity of the next read of residual buffer b
+        const uint32_t abase0 = lane_addr + TM_ABUF + (uint32_t)(8 * qd);
+        const uint32_t dbase0 = lane_addr + TM_ABUF + (uint32_t)(QCOLS * qd);
+
+        // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
+        auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
+            mbar_wait(bar_full, ring_phase);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const ulonglong2 v = lds128(st + xo[i]);
+                const ulonglong2 m = lds128(mu_addr + 16u * (uint32_t)i);
+                xc[2 * i] = sub2(v.x, m.x);
+                xc[2 * i + 1] = sub2(v.y, m.y);
+            }
+            mbar_arrive(bar_empty);
+            st += (uint32_t)SM_STAGE; bar_full += 8u; bar_empty += 8u;
+            if (++slot == NSTAGE) { slot = 0; st = ring0; bar_full = bar_full0; bar_empty = bar_empty0; ring_phase ^= 1u; }
+        };
+
+        // residual buffer b back from TMEM: my lane, my 2 x 16 columns
+        auto read_d2 = [&](uint32_t b, int64_t k, int c2) {
+            mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u);
+            dph ^= 1u << b;
             tc_fence_after();
             uint32_t v[32];
-            const uint32_t addr = lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + QCOLS * qd);
+            const uint32_t addr = dbase0 + b * (uint32_t)D2_COLS;
+#ifdef OCM_TC_EXP_NOREAD       // timing experiment only (wrong results): what does the residual read-back cost?
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+            tc_ld16(addr, v);
+            tc_wait_ld();
+#else
             tc_ld16(addr, v);
             tc_ld16(addr + STAGE_COLS, v + 16);
             tc_wait_ld();
+#endif
             if constexpr (DEBUG) {
                 if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
 #pragma unroll
@@ -354,134 +398,141 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                         g_tc_debug[(size_t)row * 1024 + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);   // p == 1024 only
                 }
             }
+#ifdef OCM_TC_EXP_NOREAD
+            q_acc += __uint_as_float(v[0]);
+#else
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
+#endif
             tc_fence_before();
         };
 
-        int slot = 0;
-        uint32_t ring_phase = 0;
         for (int64_t k = 0; k < my_tiles; ++k) {
             const uint32_t kpar = (uint32_t)(k & 1);
+            // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
+            uint32_t mu_addr = mu0;
 #pragma unroll 1
-            for (int w = 0; w < 2 * ns; ++w) {
-                const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
-                mbar_wait(BAR(B_FULL + slot), ring_phase);                 // TMA landed this stage
-                const uint8_t* st = smem + SM_OFF_RING + (size_t)slot * SM_STAGE + my_off;
-                const float* mu = s_mu + chunk * STAGE_COLS + QCOLS * qd;
-                f32x2 xc[QCOLS / 2];                                        // centred spectrum, packed pairs
+            for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(st + (((c_base + i) ^ rsw) << 4));
-                    const ulonglong2 m = *reinterpret_cast<const ulonglong2*>(mu + 4 * i);
-                    xc[2 * i] = sub2(v.x, m.x);
-                    xc[2 * i + 1] = sub2(v.y, m.y);
-                }
-                mbar_arrive(BAR(B_EMPTY + slot));                          // my part of the stage is in registers
-                if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
-
-                if (pass == 0) {
-                    const int b = chunk & 1;
-                    mbar_wait(BAR(B_AFREE + b), a_use(k, chunk) ^ 1u);          // MMAs of the buffer's previous user retired
+                for (int b = 0; b < 2; ++b) {
+                    f32x2 xc[QCOLS / 2];
+                    load_stage(mu_addr, xc);
+                    mu_addr += 4u * STAGE_COLS;
+                    mbar_wait(BAR(B_AFREE + b), aph ^ 1u);                  // MMAs of the buffer's previous user retired
                     tc_fence_after();
                     uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split3_pack2(xc[i], w1[i], w2[i], w3[i]);
-                    const uint32_t abase = lane_addr + TM_ABUF + (uint32_t)(b * 96 + 8 * qd);
+                    for (int i = 0; i < 8; ++i) {
+#ifdef OCM_TC_EXP_NOSPLIT      // timing experiment only (wrong results): what do the split instructions cost?
+                        uint32_t u0, u1; upk2(xc[i], u0, u1); w1[i] = __byte_perm(u0, u1, 0x7632); w2[i] = 0u; w3[i] = 0u;
+#else
+                        split3_pack2(xc[i], w1[i], w2[i], w3[i]);
+#endif
+                    }
+                    const uint32_t abase = abase0 + (uint32_t)(b * 96);
                     tc_st8(abase, w1);
                     tc_st8(abase + 32, w2);
                     tc_st8(abase + 64, w3);
                     tc_wait_st();
                     tc_fence_before();
                     mbar_arrive(BAR(B_AFULL + b));
-
-                    if (chunk == ns - 1) {
-                        // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
-                        mbar_wait(BAR(B_TREADY), kpar);
-                        tc_fence_after();
-                        if (qd == 0) {
-                            float t[16];
-                            {
-                                // small cross products first, then the four large (1,1) partial sums, all round-to-nearest
-                                float cross[16];
+                }
+                aph ^= 1u;
+            }
+            {
+            // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
+            mbar_wait(BAR(B_TREADY), kpar);
+            tc_fence_after();
+            if (qd == 0) {
+                float t[16];
+                {
+                    // small cross products first, then the four large (1,1) partial sums, all round-to-nearest
+                    float cross[16];
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) cross[i] = 0.f;
-                                auto add_pair = [&](uint32_t c0a, uint32_t c1a) {
-                                    uint32_t c0[16], c1[16];
-                                    tc_ld16(lane_addr + c0a, c0);
-                                    tc_ld16(lane_addr + c1a, c1);
-                                    tc_wait_ld();
+                    for (int i = 0; i < 16; ++i) cross[i] = 0.f;
+                    auto add_pair = [&](uint32_t c0a, uint32_t c1a) {
+                        uint32_t c0[16], c1[16];
+                        tc_ld16(lane_addr + c0a, c0);
+                        tc_ld16(lane_addr + c1a, c1);
+                        tc_wait_ld();
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
-                                };
+                        for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
+                    };
 #pragma unroll
-                                for (int ks = 0; ks < NACC_MAIN; ++ks) add_pair(TM_D1 + 48u * ks + 16u, TM_D1 + 48u * ks + 32u);   // (1,2) (1,3)
-                                add_pair(TM_D2 + 0u, TM_D2 + 16u);            // (2,1) (2,2) of MMA warp 0
-                                add_pair(TM_D2 + 32u, TM_D2 + 48u);           //                 MMA warp 1
-                                add_pair(TM_D3 + 0u, TM_D3 + 16u);            // (3,1) of both MMA warps
-                                uint32_t m0[16], m1[16];
-                                tc_ld16(lane_addr + TM_D1 + 0u, m0);
-                                tc_ld16(lane_addr + TM_D1 + 48u, m1);
-                                tc_wait_ld();
+                    for (int ks = 0; ks < NACC_MAIN; ++ks) add_pair(TM_D1 + 48u * ks + 16u, TM_D1 + 48u * ks + 32u);   // (1,2) (1,3)
+                    add_pair(TM_D2 + 0u, TM_D2 + 16u);            // (2,1) (2,2) of MMA warp 0
+                    add_pair(TM_D2 + 32u, TM_D2 + 48u);           //                 MMA warp 1
+                    add_pair(TM_D3 + 0u, TM_D3 + 16u);            // (3,1) of both MMA warps
+                    uint32_t m0[16], m1[16];
+                    tc_ld16(lane_addr + TM_D1 + 0u, m0);
+                    tc_ld16(lane_addr + TM_D1 + 48u, m1);
+                    tc_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
-                                tc_ld16(lane_addr + TM_D1 + 96u, m0);
-                                tc_ld16(lane_addr + TM_D1 + 144u, m1);
-                                tc_wait_ld();
+                    for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
+                    tc_ld16(lane_addr + TM_D1 + 96u, m0);
+                    tc_ld16(lane_addr + TM_D1 + 144u, m1);
+                    tc_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
-                            }
-                            float t2 = 0.f;
+                    for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
+                }
+                float t2 = 0.f;
 #pragma unroll
-                            for (int r = 0; r < NCOMP; ++r) {
-                                float s = 0.f;
+                for (int r = 0; r < NCOMP; ++r) {
+                    float s = 0.f;
 #pragma unroll
-                                for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
-                                t2 = fmaf(s, t[r], t2);
-                            }
-                            t2_row = t2;
-                            uint32_t s1[8], s2[8], s3[8];
+                    for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
+                    t2 = fmaf(s, t[r], t2);
+                }
+                t2_row = t2;
+                uint32_t s1[8], s2[8], s3[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
-                            tc_st8(lane_addr + TM_TS, s1);
-                            tc_st8(lane_addr + TM_TS + 8, s2);
-                            tc_st8(lane_addr + TM_TS + 16, s3);
-                            tc_wait_st();
-                            tc_fence_before();
-                            mbar_arrive(BAR(B_THFULL));
-                        }
-                        q_acc = 0.f;
-                    }
-                } else {
-                    const int c2 = chunk / SUBS, sub = chunk % SUBS;
-                    const int b = c2 & 1;
+                for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
+                tc_st8(lane_addr + TM_TS, s1);
+                tc_st8(lane_addr + TM_TS + 8, s2);
+                tc_st8(lane_addr + TM_TS + 16, s3);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(BAR(B_THFULL));
+            }
+            }
+            q_acc = 0.f;
+            // ---- pass 2: centred spectra into the residual accumulators, read the previous chunk back meanwhile ----
+            mu_addr = mu0;
+#pragma unroll 1
+            for (int c2 = 0; c2 < nc; ++c2) {
+                const uint32_t b = (uint32_t)c2 & 1u;
+                const uint32_t dbase = dbase0 + b * (uint32_t)D2_COLS;
+                const uint32_t bar_dfull = BAR(B_DFULL) + 8u * b;
+#pragma unroll
+                for (int sub = 0; sub < SUBS; ++sub) {
+                    f32x2 xc[QCOLS / 2];
+                    load_stage(mu_addr, xc);
+                    mu_addr += 4u * STAGE_COLS;
                     uint32_t v[QCOLS];
 #pragma unroll
                     for (int i = 0; i < QCOLS / 2; ++i) upk2(xc[i], v[2 * i], v[2 * i + 1]);
-                    tc_st16(lane_addr + TM_ABUF + (uint32_t)(b * D2_COLS + sub * STAGE_COLS + QCOLS * qd), v);
+                    tc_st16(dbase + (uint32_t)(sub * STAGE_COLS), v);
                     tc_wait_st();
                     tc_fence_before();
-                    mbar_arrive(BAR(B_DFULL + b));
-                    if (sub == SUBS - 1) {
-                        if (c2 >= 1) read_d2(k, c2 - 1);                      // previous chunk, overlapped with this chunk's MMAs
-                        if (chunk == ns - 1) {
-                            read_d2(k, c2);
-                            // combine the four column quarters of each spectrum, decide, write back
-                            if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
-                            named_bar_sync(2, NCONV);
-                            if (qd == 0) {
-                                const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
-                                if (grow < a.n) {
-                                    const float qq = (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
-                                    if (a.T2) a.T2[grow] = t2_row;
-                                    if (a.Q) a.Q[grow] = qq;
-                                    if (a.accept) a.accept[grow] = rule_distance(a.rule, t2_row * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
-                                }
-                            }
-                            named_bar_sync(2, NCONV);                         // s_q reusable
-                        }
-                    }
+                    mbar_arrive(bar_dfull);
                 }
+                if (c2 >= 1) read_d2(b ^ 1u, k, c2 - 1);                     // previous chunk, overlapped with this chunk's MMAs
+            }
+            read_d2((uint32_t)(nc - 1) & 1u, k, nc - 1);
+            {
+            // combine the four column quarters of each spectrum, decide, write back
+            if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
+            named_bar_sync(2, NCONV);
+            if (qd == 0) {
+                const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
+                if (grow < a.n) {
+                    const float qq = (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
+                    if (a.T2) a.T2[grow] = t2_row;
+                    if (a.Q) a.Q[grow] = qq;
+                    if (a.accept) a.accept[grow] = rule_distance(a.rule, t2_row * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
+                }
+            }
+            named_bar_sync(2, NCONV);                         // s_q reusable
             }
         }
     } else if (warp == W_TMA) {
@@ -525,42 +576,51 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+        uint32_t aph = 0, dph = 0;          // running phase of the A buffers (pairwise) and of MY residual buffer
         for (int64_t k = 0; k < my_tiles; ++k) {
             // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
-            for (int chunk = 0; chunk < ns; ++chunk) {
-                const int b = chunk & 1;
-                mbar_wait(BAR(B_AFULL + b), a_use(k, chunk));
-                tc_fence_after();
-                // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
-                // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
-                const uint64_t d0 = make_desc(sP + (uint32_t)chunk * (uint32_t)SM_PATOM, 16, 1024);
+            uint32_t patom = sP;
+#pragma unroll 1
+            for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int ks = 2 * mw + kk;
-                    const uint64_t d_b = d0 + (uint64_t)(((uint32_t)ks * 32u) >> 4);
-                    const uint32_t a0 = tmem + TM_ABUF + (uint32_t)(b * 96 + 8 * ks);
-                    tc_mma_ts(tmem + TM_D1 + 48u * (uint32_t)ks, a0, d_b, IDESC_N48, chunk != 0 ? 1u : 0u);
-                    tc_mma_ts(tmem + TM_D2 + 32u * (uint32_t)mw, a0 + 32, d_b, IDESC_N32, (chunk != 0 || kk != 0) ? 1u : 0u);
-                    tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (chunk != 0 || kk != 0) ? 1u : 0u);
+                for (int b = 0; b < 2; ++b) {
+                    mbar_wait(BAR(B_AFULL + b), aph);
+                    tc_fence_after();
+                    // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
+                    // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
+                    const uint64_t d0 = make_desc(patom, 16, 1024);
+                    patom += (uint32_t)SM_PATOM;
+                    const uint32_t first = (chunk | b) != 0 ? 1u : 0u;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int ks = 2 * mw + kk;
+                        const uint64_t d_b = d0 + (uint64_t)(((uint32_t)ks * 32u) >> 4);
+                        const uint32_t a0 = tmem + TM_ABUF + (uint32_t)(b * 96 + 8 * ks);
+                        tc_mma_ts(tmem + TM_D1 + 48u * (uint32_t)ks, a0, d_b, IDESC_N48, first);
+                        tc_mma_ts(tmem + TM_D2 + 32u * (uint32_t)mw, a0 + 32, d_b, IDESC_N32, (first | (uint32_t)kk) != 0 ? 1u : 0u);
+                        tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (first | (uint32_t)kk) != 0 ? 1u : 0u);
+                    }
+                    tc_commit_elect(BAR(B_AFREE + b));
                 }
-                tc_commit_elect(BAR(B_AFREE + b));
-                if (chunk == ns - 1) tc_commit_elect(BAR(B_TREADY));
+                aph ^= 1u;
             }
+            tc_commit_elect(BAR(B_TREADY));
             // ---- residual: D = xc - T * P (chunks with buffer b == mw) ------------------------------
             mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
             tc_fence_after();
+#pragma unroll 1
             for (int c2 = mw; c2 < nc; c2 += NMMAW) {
-                const int b = c2 & 1;
-                mbar_wait(BAR(B_DFULL + b), d_use(k, c2));
+                mbar_wait(BAR(B_DFULL + mw), dph);
+                dph ^= 1u;
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
                 // one MMA; the B term selects the 16-row slab (2048 B) inside the atom
                 const uint64_t d0 = make_desc(sP + (uint32_t)(c2 * (D2_COLS / 64)) * (uint32_t)SM_PATOM, lbo2, sbo2);
-                const uint32_t dst = tmem + TM_ABUF + (uint32_t)(b * D2_COLS);
+                const uint32_t dst = tmem + TM_ABUF + (uint32_t)(mw * D2_COLS);
 #pragma unroll
                 for (int m = 0; m < 6; ++m)
                     tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * 2048u) >> 4), IDESC2, 1);
-                tc_commit_elect(BAR(B_DREADY + b));
+                tc_commit_elect(BAR(B_DREADY + mw));
             }
         }
     }
