@@ -24,18 +24,29 @@
 // The residual is formed EXPLICITLY by the tensor core: the accumulator of the second product is
 // pre-loaded with the fp32 centred spectrum and the MMAs subtract T*P from it (a_negate): D = xc - P^T t.
 //
-// Data flow of one CTA (persistent, one per SM), tile = 128 spectra x 1024 wavelengths:
-//   pass 1  16 stages of 128 x 64 floats stream HBM -> smem (cp.async ring, L2 evict_last);
-//           each of 256 converter threads owns one TMEM lane (= spectrum) and 32 columns of the stage:
-//           LDS -> centre -> 3-way split -> pack -> tcgen05.st into the A-operand buffer; the MMA warp issues
-//           T[128x16] += A[128x16] * P[16x16]^T (24 tcgen05.mma per stage, A from TMEM, P from smem).
+// Data flow of one CTA (persistent, one per SM, 19 warps), tile = 128 spectra x p wavelengths:
+//   pass 1  stages of 128 x 64 floats stream HBM -> shared memory (TMA, two 128B-swizzled boxes per stage, 3-slot
+//           mbarrier ring, L2 evict_last); each of 512 converter threads owns one TMEM lane (= spectrum) and 16
+//           columns of the stage: LDS -> centre -> 3-way split -> pack -> tcgen05.st into an A-operand buffer; two
+//           MMA warps issue T[128x16] += A * P^T (3 tcgen05.mma per k-step against the stacked terms of P, 12 per
+//           stage, A from TMEM, P from shared memory).
 //   scores  T is read back once (tcgen05.ld), T2 = t^T Sinv t stays in a register, t is split and
 //           stored as the A operand of the second product.
 //   pass 2  the same tile is streamed again -- from L2, where pass 1 left it (evict_first now) --
-//           centred spectra go straight into the accumulator D[128x128] (tcgen05.st), the MMA warp issues
+//           centred spectra go straight into the accumulator D[128x128] (tcgen05.st), the MMA warps issue
 //           D -= T * P[:, chunk] (6 MMAs per 128 columns, the same smem copy of P read MN-major), threads
 //           read D back and accumulate Q = sum r^2.
 // Only T2, Q and the decision go back to HBM.  All hand-offs are mbarriers; every wait is bounded.
+//
+// Measured on the B200 (profiles/r01_score_tc_v6.md): 8.9-9.0 ms per 10 M x 1024 spectra for a launch on its own = 70 %
+// of the measured HBM peak, DRAM traffic 42.3 GB for 41.0 GB algorithmic (the second read is served by L2); in a long
+// back-to-back run the board's 1000 W power cap pulls the SM clock down and the same launch takes 10.3-10.8 ms
+// (tools/step_times.py) -- the kernel is instruction- and latency-bound in its converter warps, not HBM-bound.
+// Tried and rejected, each A/B-timed on the same box (DESIGN.md has the numbers): a 7-slot ring of single boxes, a
+// 4/5-slot ring at smaller p (ring depth is not the limiter), TMA L2 prefetch ahead of the ring, back-off sleeps in the
+// polling loops, reading pass 2 straight from L2 into registers (row-strided 16 B loads: 3x slower), and interleaving
+// pass 1 of tile s with pass 2 of tile s-1 (the kept working set doubles to 76 MB, L2 hit rate falls from 49 % to
+// 35 %, DRAM traffic +50 %).
 #include "ocm_common.cuh"
 
 #include <cuda.h>
@@ -381,16 +392,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             tc_fence_after();
             uint32_t v[32];
             const uint32_t addr = dbase0 + b * (uint32_t)D2_COLS;
-#ifdef OCM_TC_EXP_NOREAD       // timing experiment only (wrong results): what does the residual read-back cost?
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-            tc_ld16(addr, v);
-            tc_wait_ld();
-#else
             tc_ld16(addr, v);
             tc_ld16(addr + STAGE_COLS, v + 16);
             tc_wait_ld();
-#endif
             if constexpr (DEBUG) {
                 if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
 #pragma unroll
@@ -398,12 +402,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                         g_tc_debug[(size_t)row * 1024 + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);   // p == 1024 only
                 }
             }
-#ifdef OCM_TC_EXP_NOREAD
-            q_acc += __uint_as_float(v[0]);
-#else
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
-#endif
             tc_fence_before();
         };
 
@@ -423,11 +423,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-#ifdef OCM_TC_EXP_NOSPLIT      // timing experiment only (wrong results): what do the split instructions cost?
-                        uint32_t u0, u1; upk2(xc[i], u0, u1); w1[i] = __byte_perm(u0, u1, 0x7632); w2[i] = 0u; w3[i] = 0u;
-#else
                         split3_pack2(xc[i], w1[i], w2[i], w3[i]);
-#endif
                     }
                     const uint32_t abase = abase0 + (uint32_t)(b * 96);
                     tc_st8(abase, w1);
