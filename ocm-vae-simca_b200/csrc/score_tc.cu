@@ -108,6 +108,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+template <int OFF>
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar) {      // [bar + OFF]: the offset rides in the instruction
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar), "n"(OFF) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -331,6 +335,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const int r = i / NCOMP, c = i % NCOMP;
         s_S[i] = (r < a.A && c < a.A) ? a.Sinv[r * a.A + c] : 0.f;
     }
+    // cov(T) of PCA scores is diagonal, and so is the Sinv our own fit passes (diag(1/lambda)): then T2 is 16 FMAs per
+    // spectrum instead of a 16 x 16 quadratic form.  Exact test (every off-diagonal entry == 0), general path otherwise.
+    int offdiag = 0;
+    for (int i = tid; i < a.A * a.A; i += NTHREADS) offdiag |= (i / a.A != i % a.A && a.Sinv[i] != 0.f) ? 1 : 0;
+    const bool s_diag = __syncthreads_or(offdiag) == 0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -362,9 +371,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) xo[i] = (uint32_t)(((c_base + i) ^ rsw) << 4);
         const uint32_t mu0 = sb + (uint32_t)SM_OFF_MU + 4u * (uint32_t)(QCOLS * qd);
-        const uint32_t bar_full0 = BAR(B_FULL), bar_empty0 = BAR(B_EMPTY);
-        uint32_t st = ring0, bar_full = bar_full0, bar_empty = bar_empty0, ring_phase = 0;
-        int slot = 0;
+        const uint32_t bar_full0 = BAR(B_FULL), bar_full_end = BAR(B_FULL + NSTAGE);
+        uint32_t st = ring0, bar_full = bar_full0, ring_phase = 0;      // the slot is implied by its FULL barrier address
         uint32_t aph = 0;      // parity of the current use of the A buffers (they advance in pairs)
         uint32_t dph = 0;      // bit b: parity of the next read of residual buffer b
         const uint32_t abase0 = lane_addr + TM_ABUF + (uint32_t)(8 * qd);
@@ -380,9 +388,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 xc[2 * i] = sub2(v.x, m.x);
                 xc[2 * i + 1] = sub2(v.y, m.y);
             }
-            mbar_arrive(bar_empty);
-            st += (uint32_t)SM_STAGE; bar_full += 8u; bar_empty += 8u;
-            if (++slot == NSTAGE) { slot = 0; st = ring0; bar_full = bar_full0; bar_empty = bar_empty0; ring_phase ^= 1u; }
+            mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
+            st += (uint32_t)SM_STAGE; bar_full += 8u;
+            if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
         };
 
         // residual buffer b back from TMEM: my lane, my 2 x 16 columns
@@ -472,12 +480,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
                 }
                 float t2 = 0.f;
+                if (s_diag) {
 #pragma unroll
-                for (int r = 0; r < NCOMP; ++r) {
-                    float s = 0.f;
+                    for (int r = 0; r < NCOMP; ++r) t2 = fmaf(s_S[r * (NCOMP + 1)] * t[r], t[r], t2);
+                } else {
 #pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
-                    t2 = fmaf(s, t[r], t2);
+                    for (int r = 0; r < NCOMP; ++r) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int c = 0; c < NCOMP; ++c) s = fmaf(s_S[r * NCOMP + c], t[c], s);
+                        t2 = fmaf(s, t[r], t2);
+                    }
                 }
                 t2_row = t2;
                 uint32_t s1[8], s2[8], s3[8];

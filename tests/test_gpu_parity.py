@@ -364,7 +364,9 @@ def test_tensor_core_kernel_matches_oracle(torch):
                     (20000, 5, 700), (9000, 12, 1052), (30000, 10, 1152), (3000, 4, 64), (7000, 8, 520)):
         X = synth.make_spectra_device(n, p, dev, seed=n % 97 + A)
         pca = engine.fit_pca(X[:2000].contiguous(), None, A)
-        Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev)) + (1e-3 if A > 1 else 0.0)
+        # full Sinv (general quadratic form) on most shapes, exactly diagonal Sinv (the kernel's 16-FMA path) on the others
+        full = A > 1 and n % 3 != 0
+        Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev)) + (1e-3 if full else 0.0)
         mu32, P32 = pca.arrays32()
         S32 = Sinv.float().contiguous()
         prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
