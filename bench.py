@@ -308,7 +308,7 @@ def main():
         prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=float(ct), cq=float(cq), dlim=float(lim.D_limit))
         vp = lambda t: C.c_void_p(t.data_ptr())
         call = lambda: native.check(native.lib().ocm_simca_score_host_f32(
-            vp(hX), er, p, p, vp(h_mu), vp(h_P), vp(h_S), C.byref(prm), 1 << 17, vp(hT2), vp(hQ), vp(hA)), "host score")
+            vp(hX), er, p, p, vp(h_mu), vp(h_P), vp(h_S), C.byref(prm), 0, vp(hT2), vp(hQ), vp(hA)), "host score")
         call()
         torch.cuda.synchronize(); barrier()
         esteps = max(2, min(args.steps, 5))

@@ -189,13 +189,15 @@ int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_t ldz,
                          float* d2, float* q, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end call bench.py times as `e2e`) -------------
- * Scores h_X (HOST, pageable or pinned) in row chunks, overlapping H2D copies with the
- * kernel on two internal streams, and writes h_T2 / h_Q / h_accept (HOST).  Allocates and
- * frees its own staging buffers and synchronises before returning. */
+ * Scores h_X (HOST, pageable or pinned) in row chunks (chunk_rows <= 0: 65536), overlapping H2D copies with the
+ * kernel on two internal streams, and writes h_T2 / h_Q / h_accept (HOST).  Synchronises before returning.  Its
+ * device staging buffers and streams are a per-process workspace kept between calls (calls are serialised);
+ * ocm_simca_host_release() frees it. */
 int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, int64_t ldx,
                              const float* h_mu, const float* h_P, const float* h_Sinv,
                              const ocm_score_params* h_params, int64_t chunk_rows,
                              float* h_T2, float* h_Q, uint8_t* h_accept);
+int ocm_simca_host_release(void);
 
 #ifdef __cplusplus
 }

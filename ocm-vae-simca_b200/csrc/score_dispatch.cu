@@ -1,6 +1,8 @@
 // Public scoring entry points: path selection and the host-buffer convenience call.
 #include "ocm_common.cuh"
 
+#include <mutex>
+
 extern "C" int ocm_simca_score_simt_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
                                         const float*, const ocm_score_params*, float*, float*, uint8_t*, float*, void*);
 extern "C" int ocm_simca_score_tc_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
@@ -23,8 +25,41 @@ extern "C" int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t
     return ocm_simca_score_simt_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
 }
 
-// Host buffers in, host buffers out: chunked, double-buffered over two streams so the H2D
-// copy of chunk i+1 overlaps the kernel of chunk i.  This is the call bench.py times as e2e.
+// Host buffers in, host buffers out: chunked, double-buffered over two streams so the H2D copy of chunk i+1 overlaps the
+// kernel of chunk i.  This is the call bench.py times as e2e.  The staging buffers and the two streams are a
+// per-device workspace that is kept between calls (grown on demand, released by ocm_simca_host_release): allocating
+// and freeing ~1 GB per call costs milliseconds and a device-wide synchronisation.  Contiguous rows go as ONE 1-D copy
+// per chunk (a 2-D copy of 128 Ki rows x 4 KiB ran at 19 GB/s on the B200 box where the 1-D copy reaches 55 GB/s).
+namespace {
+struct HostWorkspace {
+    int device = -1;
+    size_t x_bytes = 0, out_rows = 0, model_floats = 0;
+    float* d_X[2] = {nullptr, nullptr};
+    float* d_T2[2] = {nullptr, nullptr};
+    float* d_Q[2] = {nullptr, nullptr};
+    uint8_t* d_acc[2] = {nullptr, nullptr};
+    float* d_model = nullptr;                 // mu | P | Sinv
+    cudaStream_t st[2] = {nullptr, nullptr};
+    void release() {
+        for (int b = 0; b < 2; ++b) {
+            if (st[b]) { cudaStreamSynchronize(st[b]); cudaStreamDestroy(st[b]); st[b] = nullptr; }
+            cudaFree(d_X[b]); cudaFree(d_T2[b]); cudaFree(d_Q[b]); cudaFree(d_acc[b]);
+            d_X[b] = d_T2[b] = d_Q[b] = nullptr; d_acc[b] = nullptr;
+        }
+        cudaFree(d_model); d_model = nullptr;
+        x_bytes = out_rows = model_floats = 0; device = -1;
+    }
+};
+HostWorkspace g_ws;
+std::mutex g_ws_mutex;
+}  // namespace
+
+extern "C" int ocm_simca_host_release(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    g_ws.release();
+    return 0;
+}
+
 extern "C" int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, int64_t ldx,
                                         const float* h_mu, const float* h_P, const float* h_Sinv,
                                         const ocm_score_params* hp, int64_t chunk_rows,
@@ -34,52 +69,62 @@ extern "C" int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, 
     OCM_REQUIRE(n >= 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
     OCM_REQUIRE(hp->A >= 1 && hp->A <= 64, OCM_ELIMIT, "n_components must be 1..64");
     if (n == 0) return 0;
-    if (chunk_rows <= 0) chunk_rows = 1 << 17;
+    if (chunk_rows <= 0) chunk_rows = 1 << 16;
     if (chunk_rows > n) chunk_rows = n;
     const int A = hp->A;
-    float *d_mu = nullptr, *d_P = nullptr, *d_S = nullptr;
-    float* d_X[2] = {nullptr, nullptr};
-    float* d_T2[2] = {nullptr, nullptr};
-    float* d_Q[2] = {nullptr, nullptr};
-    uint8_t* d_acc[2] = {nullptr, nullptr};
-    cudaStream_t st[2] = {nullptr, nullptr};
-    int rc = 0;
-    auto cleanup = [&]() {
-        for (int b = 0; b < 2; ++b) {
-            if (st[b]) { cudaStreamSynchronize(st[b]); cudaStreamDestroy(st[b]); }
-            cudaFree(d_X[b]); cudaFree(d_T2[b]); cudaFree(d_Q[b]); cudaFree(d_acc[b]);
-        }
-        cudaFree(d_mu); cudaFree(d_P); cudaFree(d_S);
-    };
+    std::lock_guard<std::mutex> lock(g_ws_mutex);      // one host-buffer call at a time per process
+    HostWorkspace& w = g_ws;
 #define OCM_TRY(call)                                                                        \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                   \
-        set_error("%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return (int)e_; } } while (0)
-    OCM_TRY(cudaMalloc(&d_mu, sizeof(float) * p));
-    OCM_TRY(cudaMalloc(&d_P, sizeof(float) * (size_t)A * p));
-    OCM_TRY(cudaMalloc(&d_S, sizeof(float) * (size_t)A * A));
-    OCM_TRY(cudaMemcpy(d_mu, h_mu, sizeof(float) * p, cudaMemcpyHostToDevice));
-    OCM_TRY(cudaMemcpy(d_P, h_P, sizeof(float) * (size_t)A * p, cudaMemcpyHostToDevice));
-    OCM_TRY(cudaMemcpy(d_S, h_Sinv, sizeof(float) * (size_t)A * A, cudaMemcpyHostToDevice));
+        set_error("%s: %s", #call, cudaGetErrorString(e_)); w.release(); return (int)e_; } } while (0)
+    int dev = 0;
+    OCM_TRY(cudaGetDevice(&dev));
+    if (w.device != dev) { w.release(); w.device = dev; }
+    const size_t need_x = sizeof(float) * (size_t)chunk_rows * p, need_model = (size_t)p + (size_t)A * p + (size_t)A * A;
     for (int b = 0; b < 2; ++b) {
-        OCM_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-        OCM_TRY(cudaMalloc(&d_X[b], sizeof(float) * (size_t)chunk_rows * p));
-        OCM_TRY(cudaMalloc(&d_T2[b], sizeof(float) * chunk_rows));
-        OCM_TRY(cudaMalloc(&d_Q[b], sizeof(float) * chunk_rows));
-        OCM_TRY(cudaMalloc(&d_acc[b], chunk_rows));
+        if (!w.st[b]) OCM_TRY(cudaStreamCreateWithFlags(&w.st[b], cudaStreamNonBlocking));
+        if (w.x_bytes < need_x) { OCM_TRY(cudaFree(w.d_X[b])); w.d_X[b] = nullptr; OCM_TRY(cudaMalloc(&w.d_X[b], need_x)); }
+        if (w.out_rows < (size_t)chunk_rows) {
+            OCM_TRY(cudaFree(w.d_T2[b])); OCM_TRY(cudaFree(w.d_Q[b])); OCM_TRY(cudaFree(w.d_acc[b]));
+            w.d_T2[b] = w.d_Q[b] = nullptr; w.d_acc[b] = nullptr;
+            OCM_TRY(cudaMalloc(&w.d_T2[b], sizeof(float) * chunk_rows));
+            OCM_TRY(cudaMalloc(&w.d_Q[b], sizeof(float) * chunk_rows));
+            OCM_TRY(cudaMalloc(&w.d_acc[b], chunk_rows));
+        }
     }
+    if (w.x_bytes < need_x) w.x_bytes = need_x;
+    if (w.out_rows < (size_t)chunk_rows) w.out_rows = (size_t)chunk_rows;
+    if (w.model_floats < need_model) {
+        OCM_TRY(cudaFree(w.d_model)); w.d_model = nullptr;
+        OCM_TRY(cudaMalloc(&w.d_model, sizeof(float) * need_model));
+        w.model_floats = need_model;
+    }
+    float* d_mu = w.d_model; float* d_P = d_mu + p; float* d_S = d_P + (size_t)A * p;
+    // the model goes first on BOTH streams' timeline: copy on stream 0, stream 1 waits for it
+    OCM_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(float) * p, cudaMemcpyHostToDevice, w.st[0]));
+    OCM_TRY(cudaMemcpyAsync(d_P, h_P, sizeof(float) * (size_t)A * p, cudaMemcpyHostToDevice, w.st[0]));
+    OCM_TRY(cudaMemcpyAsync(d_S, h_Sinv, sizeof(float) * (size_t)A * A, cudaMemcpyHostToDevice, w.st[0]));
+    cudaEvent_t model_ready;
+    OCM_TRY(cudaEventCreateWithFlags(&model_ready, cudaEventDisableTiming));
+    cudaError_t e_rec = cudaEventRecord(model_ready, w.st[0]);
+    if (e_rec == cudaSuccess) e_rec = cudaStreamWaitEvent(w.st[1], model_ready, 0);
+    cudaEventDestroy(model_ready);                     // released by the runtime once the wait has been satisfied
+    OCM_TRY(e_rec);
     int b = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, b ^= 1) {
         const int64_t m = (n - r0 < chunk_rows) ? n - r0 : chunk_rows;
-        OCM_TRY(cudaMemcpy2DAsync(d_X[b], sizeof(float) * p, h_X + r0 * ldx, sizeof(float) * ldx,
-                                  sizeof(float) * p, (size_t)m, cudaMemcpyHostToDevice, st[b]));
-        rc = ocm_simca_score_f32(d_X[b], m, p, p, d_mu, d_P, d_S, hp, d_T2[b], d_Q[b], d_acc[b], nullptr, st[b]);
-        if (rc) { cleanup(); return rc; }
-        if (h_T2) OCM_TRY(cudaMemcpyAsync(h_T2 + r0, d_T2[b], sizeof(float) * m, cudaMemcpyDeviceToHost, st[b]));
-        if (h_Q) OCM_TRY(cudaMemcpyAsync(h_Q + r0, d_Q[b], sizeof(float) * m, cudaMemcpyDeviceToHost, st[b]));
-        if (h_accept) OCM_TRY(cudaMemcpyAsync(h_accept + r0, d_acc[b], (size_t)m, cudaMemcpyDeviceToHost, st[b]));
+        if (ldx == p)
+            OCM_TRY(cudaMemcpyAsync(w.d_X[b], h_X + r0 * ldx, sizeof(float) * (size_t)m * p, cudaMemcpyHostToDevice, w.st[b]));
+        else
+            OCM_TRY(cudaMemcpy2DAsync(w.d_X[b], sizeof(float) * p, h_X + r0 * ldx, sizeof(float) * ldx,
+                                      sizeof(float) * p, (size_t)m, cudaMemcpyHostToDevice, w.st[b]));
+        const int rc = ocm_simca_score_f32(w.d_X[b], m, p, p, d_mu, d_P, d_S, hp, w.d_T2[b], w.d_Q[b], w.d_acc[b], nullptr, w.st[b]);
+        if (rc) { w.release(); return rc; }
+        if (h_T2) OCM_TRY(cudaMemcpyAsync(h_T2 + r0, w.d_T2[b], sizeof(float) * m, cudaMemcpyDeviceToHost, w.st[b]));
+        if (h_Q) OCM_TRY(cudaMemcpyAsync(h_Q + r0, w.d_Q[b], sizeof(float) * m, cudaMemcpyDeviceToHost, w.st[b]));
+        if (h_accept) OCM_TRY(cudaMemcpyAsync(h_accept + r0, w.d_acc[b], (size_t)m, cudaMemcpyDeviceToHost, w.st[b]));
     }
-    for (int k = 0; k < 2; ++k) OCM_TRY(cudaStreamSynchronize(st[k]));
+    for (int k = 0; k < 2; ++k) OCM_TRY(cudaStreamSynchronize(w.st[k]));
 #undef OCM_TRY
-    cleanup();
     return 0;
 }
