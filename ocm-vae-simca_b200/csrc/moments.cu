@@ -290,10 +290,22 @@ int gram_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_
         // FP64 tensor-pipe kernel: 128x128 tiles, one CTA per SM, K split to fill the machine
         const int ntd = (p + DT - 1) / DT;
         const int tiles = ntd * (ntd + 1) / 2;
-        int64_t splits = sm_count() / tiles;
-        if (splits < 1) splits = 1;
-        const int64_t max_splits = (n + 255) / 256;
-        if (splits > max_splits) splits = max_splits;
+        // K splits: the CTAs take equal time, so pick the split count whose tiles * splits fills whole waves of SMs
+        // best (p = 2048: 136 tiles -> 37 splits = exactly 34 waves of 148 instead of 136 CTAs on 148 SMs), with at
+        // least 4096 rows per CTA so the 128 x 128 atomic epilogue stays negligible
+        const int sms = sm_count();
+        int64_t max_splits = n / 4096;
+        if (max_splits < 1) max_splits = sms / tiles > 0 && n >= 512 ? sms / tiles : 1;
+        if (max_splits > 64) max_splits = 64;
+        const int64_t rows_cap = (n + 255) / 256;
+        if (max_splits > rows_cap) max_splits = rows_cap;
+        int64_t splits = 1;
+        double best = 0.0;
+        for (int64_t sp = 1; sp <= max_splits; ++sp) {
+            const int64_t ctas = (int64_t)tiles * sp, waves = (ctas + sms - 1) / sms;
+            const double eff = (double)ctas / (double)(waves * sms);
+            if (eff > best + 0.01) { best = eff; splits = sp; }
+        }
         int64_t rps = (n + splits - 1) / splits;
         rps = (rps + DK - 1) / DK * DK;
         splits = (n + rps - 1) / rps;
