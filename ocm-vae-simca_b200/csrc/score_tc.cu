@@ -203,6 +203,11 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 // 3-way split of a packed pair: the two remainders are computed with one packed subtract each
 __device__ __forceinline__ void split3_pack2(f32x2 x, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
     uint32_t u0, u1, v0, v1, s0, s1;
@@ -251,8 +256,8 @@ struct Args {
 };
 
 // mbarrier slots
-enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE + NABUF, B_DFULL = 2 * NSTAGE + 2 * NABUF,
-       B_DREADY = B_DFULL + 2, B_TREADY = B_DFULL + 4, B_THFULL = B_DFULL + 5, B_COUNT = B_DFULL + 6 };
+enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE + NABUF, B_DFREE = 2 * NSTAGE + 2 * NABUF,
+       B_DREADY = B_DFREE + 2, B_TREADY = B_DFREE + 4, B_THFULL = B_DFREE + 5, B_COUNT = B_DFREE + 6 };
 
 static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one D1 accumulator per k-step of a stage");
 static_assert(NABUF == 2 && P_MAX % D2_COLS == 0, "two A buffers; residual chunks of 128 columns");
@@ -292,7 +297,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), NCONV); }
         for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), NMMAW); }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), NCONV * SUBS); mbar_init(BAR(B_DREADY + b), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFREE + b), NCONV); mbar_init(BAR(B_DREADY + b), 1); }
         mbar_init(BAR(B_TREADY), NMMAW);
         mbar_init(BAR(B_THFULL), TILE_M);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -393,28 +398,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
         };
 
-        // residual buffer b back from TMEM: my lane, my 2 x 16 columns
-        auto read_d2 = [&](uint32_t b, int64_t k, int c2) {
-            mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u);
-            dph ^= 1u << b;
-            tc_fence_after();
-            uint32_t v[32];
-            const uint32_t addr = dbase0 + b * (uint32_t)D2_COLS;
-            tc_ld16(addr, v);
-            tc_ld16(addr + STAGE_COLS, v + 16);
-            tc_wait_ld();
-            if constexpr (DEBUG) {
-                if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        g_tc_debug[(size_t)row * 1024 + c2 * D2_COLS + (i >> 4) * STAGE_COLS + QCOLS * qd + (i & 15)] = __uint_as_float(v[i]);   // p == 1024 only
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { const float r = __uint_as_float(v[i]); q_acc = fmaf(r, r, q_acc); }
-            tc_fence_before();
-        };
-
         for (int64_t k = 0; k < my_tiles; ++k) {
             const uint32_t kpar = (uint32_t)(k & 1);
             // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
@@ -504,30 +487,52 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 mbar_arrive(BAR(B_THFULL));
             }
             }
-            q_acc = 0.f;
-            // ---- pass 2: centred spectra into the residual accumulators, read the previous chunk back meanwhile ----
+            // ---- pass 2: the MMA warps rebuild T * P chunk by chunk in TMEM (they need nothing from us but a free
+            // buffer); we stream the tile again, subtract the reconstruction from the centred spectrum in registers and
+            // accumulate Q = sum r^2 ------------------------------------------------------------------------------
+            f32x2 q2 = pk2(0u, 0u);
             mu_addr = mu0;
 #pragma unroll 1
             for (int c2 = 0; c2 < nc; ++c2) {
                 const uint32_t b = (uint32_t)c2 & 1u;
                 const uint32_t dbase = dbase0 + b * (uint32_t)D2_COLS;
-                const uint32_t bar_dfull = BAR(B_DFULL) + 8u * b;
 #pragma unroll
                 for (int sub = 0; sub < SUBS; ++sub) {
                     f32x2 xc[QCOLS / 2];
                     load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
+                    if (sub == 0) {
+                        mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u);    // the chunk's six MMAs have retired
+                        dph ^= 1u << b;
+                        tc_fence_after();
+                    }
                     uint32_t v[QCOLS];
+                    tc_ld16(dbase + (uint32_t)(sub * STAGE_COLS), v);
+                    tc_wait_ld();
+                    if (sub == SUBS - 1) {
+                        tc_fence_before();
+                        mbar_arrive(BAR(B_DFREE) + 8u * b);                    // my part of the buffer is in registers
+                    }
 #pragma unroll
-                    for (int i = 0; i < QCOLS / 2; ++i) upk2(xc[i], v[2 * i], v[2 * i + 1]);
-                    tc_st16(dbase + (uint32_t)(sub * STAGE_COLS), v);
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(bar_dfull);
+                    for (int i = 0; i < QCOLS / 2; ++i) {
+                        const f32x2 r = sub2(xc[i], pk2(v[2 * i], v[2 * i + 1]));
+                        q2 = fma2(r, r, q2);
+                        if constexpr (DEBUG) {
+                            if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {       // residual of tile 0 (p <= 1024)
+                                uint32_t r0, r1;
+                                upk2(r, r0, r1);
+                                float* d = g_tc_debug + (size_t)row * 1024 + c2 * D2_COLS + sub * STAGE_COLS + QCOLS * qd + 2 * i;
+                                d[0] = __uint_as_float(r0); d[1] = __uint_as_float(r1);
+                            }
+                        }
+                    }
                 }
-                if (c2 >= 1) read_d2(b ^ 1u, k, c2 - 1);                     // previous chunk, overlapped with this chunk's MMAs
             }
-            read_d2((uint32_t)(nc - 1) & 1u, k, nc - 1);
+            {
+                uint32_t qa, qb;
+                upk2(q2, qa, qb);
+                q_acc = __uint_as_float(qa) + __uint_as_float(qb);
+            }
             {
             // combine the four column quarters of each spectrum, decide, write back
             if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
@@ -580,7 +585,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false);
         constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false);
         const unsigned int variant = DEBUG ? g_tc_variant : 0u;
-        const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, !(variant & 1u), !(variant & 4u));
+        const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, (variant & 1u) != 0, !(variant & 4u));
         const uint32_t lbo2 = (variant & 2u) ? 1024u : (uint32_t)SM_PATOM, sbo2 = (variant & 2u) ? (uint32_t)SM_PATOM : 1024u;
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
@@ -614,12 +619,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 aph ^= 1u;
             }
             tc_commit_elect(BAR(B_TREADY));
-            // ---- residual: D = xc - T * P (chunks with buffer b == mw) ------------------------------
+            // ---- reconstruction: D = T * P (chunks with buffer b == mw) -----------------------------
             mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
             tc_fence_after();
 #pragma unroll 1
             for (int c2 = mw; c2 < nc; c2 += NMMAW) {
-                mbar_wait(BAR(B_DFULL + mw), dph);
+                mbar_wait(BAR(B_DFREE + mw), dph ^ 1u);                     // every converter has read the buffer's previous chunk
                 dph ^= 1u;
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
@@ -628,7 +633,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 const uint32_t dst = tmem + TM_ABUF + (uint32_t)(mw * D2_COLS);
 #pragma unroll
                 for (int m = 0; m < 6; ++m)
-                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * 2048u) >> 4), IDESC2, 1);
+                    tc_mma_ts(dst, tmem + TM_TS + 8u * (uint32_t)pa[m], d0 + (uint64_t)(((uint32_t)pb[m] * 2048u) >> 4), IDESC2, m != 0 ? 1u : 0u);
                 tc_commit_elect(BAR(B_DREADY + mw));
             }
         }
