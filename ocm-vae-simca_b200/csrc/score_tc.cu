@@ -21,8 +21,8 @@
 // predecessor waits for it (~100 cycles measured for these small N = 16 MMAs, which made the MMA warp the
 // bottleneck), so the five cross products get two accumulators each as well: 14 accumulators, and no two
 // consecutive MMAs of the projection touch the same one; the converter thread adds them with round-to-nearest.
-// The residual is formed EXPLICITLY by the tensor core: the accumulator of the second product is
-// pre-loaded with the fp32 centred spectrum and the MMAs subtract T*P from it (a_negate): D = xc - P^T t.
+// The residual is formed EXPLICITLY, r = xc - P^T t element by element (never as |xc|^2 - |t|^2, which cancels):
+// the tensor core rebuilds P^T t in TMEM and the converter threads subtract it from the fp32 centred spectrum.
 //
 // Data flow of one CTA (persistent, one per SM, 19 warps), tile = 128 spectra x p wavelengths:
 //   pass 1  stages of 128 x 64 floats stream HBM -> shared memory (TMA, two 128B-swizzled boxes per stage, 3-slot
@@ -32,15 +32,15 @@
 //           stage, A from TMEM, P from shared memory).
 //   scores  T is read back once (tcgen05.ld), T2 = t^T Sinv t stays in a register, t is split and
 //           stored as the A operand of the second product.
-//   pass 2  the same tile is streamed again -- from L2, where pass 1 left it (evict_first now) --
-//           centred spectra go straight into the accumulator D[128x128] (tcgen05.st), the MMA warps issue
-//           D -= T * P[:, chunk] (6 MMAs per 128 columns, the same smem copy of P read MN-major), threads
-//           read D back and accumulate Q = sum r^2.
+//   pass 2  the MMA warps rebuild D[128x128] = T * P[:, chunk] chunk by chunk (6 MMAs per 128 columns, the same smem
+//           copy of P read MN-major, two TMEM buffers); the same tile is streamed again -- from L2, where pass 1 left
+//           it (evict_first now) -- and the converters read D back (tcgen05.ld), subtract it from the centred
+//           spectrum in registers and accumulate Q = sum r^2.
 // Only T2, Q and the decision go back to HBM.  All hand-offs are mbarriers; every wait is bounded.
 //
-// Measured on the B200 (profiles/r01_score_tc_v6.md): 8.9-9.0 ms per 10 M x 1024 spectra for a launch on its own = 70 %
-// of the measured HBM peak, DRAM traffic 42.3 GB for 41.0 GB algorithmic (the second read is served by L2); in a long
-// back-to-back run the board's 1000 W power cap pulls the SM clock down and the same launch takes 10.3-10.8 ms
+// Measured on the B200 (profiles/r01_score_tc_v11.md): 8.65-8.8 ms per 10 M x 1024 spectra for a launch on its own =
+// 72 % of the measured HBM peak, DRAM traffic 42.1 GB for 41.0 GB algorithmic (the second read is served by L2); in a
+// long back-to-back run the board's 1000 W power cap pulls the SM clock down and the same launch takes 9.2-10.0 ms
 // (tools/step_times.py) -- the kernel is instruction- and latency-bound in its converter warps, not HBM-bound.
 // Tried and rejected, each A/B-timed on the same box (DESIGN.md has the numbers): a 7-slot ring of single boxes, a
 // 4/5-slot ring at smaller p (ring depth is not the limiter), TMA L2 prefetch ahead of the ring, back-off sleeps in the
