@@ -113,7 +113,7 @@ gram_f64_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict_
 
 // ---------------------------------------------------------------- fp64 tensor-core Gram ---
 // The same contraction on the FP64 tensor pipe (DMMA, mma.sync m8n8k4 f64): 128x128 output tile per CTA
-// (upper-triangle tiles only), 8 warps of 64x32, 16-row K stages double-buffered in shared memory, the next
+// (upper-triangle tiles only), 8 warps of 64x32, 32- (fp32) or 16-row (fp64) K stages double-buffered in shared memory, the next
 // stage prefetched into registers while the current one is multiplied.  Why fp64 and not the tcgen05 low-precision
 // kinds: the 5th-gen tensor core adds into its fp32 accumulator with truncation, which biases a chain of k
 // accumulations by ~k * 2^-25 relative (measured in score_tc.cu: 384 chained MMAs -> -1.1e-5).  On strongly
@@ -121,7 +121,7 @@ gram_f64_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict_
 // eigenvalues a SIMCA model needs (lambda_20 / lambda_1 ~ 2e-4), and an on-chip fp64 tile (128x256 doubles =
 // 256 KB) does not exist to flush short chains into.  DMMA keeps every product and sum in fp64.
 constexpr int DT = 128;        // tile edge
-constexpr int DK = 16;         // rows per stage
+template <typename T> struct GramStage { static constexpr int DK = sizeof(T) == 4 ? 32 : 16; };   // rows per stage (fp32 rows are half the prefetch registers)
 constexpr int DPITCH = DT + 4; // doubles; +32 B per row keeps the fragment LDS.64 conflict free
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256, 1)
 gram_dmma_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx,
                  int64_t n, int p, const double* __restrict__ shift, double* __restrict__ G,
                  int64_t rows_per_split) {
+    constexpr int DK = GramStage<T>::DK, NH = DK / 8;
     extern __shared__ __align__(16) double sm_d[];
     double (*As)[DK][DPITCH] = reinterpret_cast<double (*)[DK][DPITCH]>(sm_d);
     double (*Bs)[DK][DPITCH] = reinterpret_cast<double (*)[DK][DPITCH]>(sm_d + 2 * DK * DPITCH);
@@ -164,32 +165,41 @@ gram_dmma_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict
         shA[e] = (shift && i0 + lc + e < p) ? shift[i0 + lc + e] : 0.0;
         shB[e] = (shift && j0 + lc + e < p) ? shift[j0 + lc + e] : 0.0;
     }
-    double ra[2][4], rb[2][4];
+    // The loads of the NEXT stage are issued before the MMAs of the current one and must stay raw until the stash: the
+    // first version converted and shifted right at the fetch, which put the wait for the loads in front of the MMAs
+    // (ncu: 27 % of all warp samples on that line).
+    T ra[NH][4], rb[NH][4];
+    bool rok[NH];
+    bool cokA[4], cokB[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { cokA[e] = i0 + lc + e < p; cokB[e] = j0 + lc + e < p; }
     auto fetch = [&](int64_t r0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NH; ++h) {
             const int64_t r = r0 + lk0 + 8 * h;
-            if (r < r_end) {
-                const int64_t row = row_idx ? row_idx[r] : r;
-                const T* xr = X + row * ldx;
+            rok[h] = r < r_end;
+            const int64_t row = rok[h] ? (row_idx ? row_idx[r] : r) : 0;
+            const T* xr = X + row * ldx;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ra[h][e] = (i0 + lc + e < p) ? (double)xr[i0 + lc + e] - shA[e] : 0.0;
-                    rb[h][e] = (j0 + lc + e < p) ? (double)xr[j0 + lc + e] - shB[e] : 0.0;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ra[h][e] = rb[h][e] = 0.0;
+            for (int e = 0; e < 4; ++e) {
+                ra[h][e] = (rok[h] && cokA[e]) ? xr[i0 + lc + e] : T(0);
+                rb[h][e] = (rok[h] && cokB[e]) ? xr[j0 + lc + e] : T(0);
             }
         }
     };
     auto stash = [&](int buf) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NH; ++h) {
+            double va[4], vb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                va[e] = (rok[h] && cokA[e]) ? (double)ra[h][e] - shA[e] : 0.0;
+                vb[e] = (rok[h] && cokB[e]) ? (double)rb[h][e] - shB[e] : 0.0;
+            }
             double2* da = reinterpret_cast<double2*>(&As[buf][lk0 + 8 * h][lc]);
             double2* db = reinterpret_cast<double2*>(&Bs[buf][lk0 + 8 * h][lc]);
-            da[0] = make_double2(ra[h][0], ra[h][1]); da[1] = make_double2(ra[h][2], ra[h][3]);
-            db[0] = make_double2(rb[h][0], rb[h][1]); db[1] = make_double2(rb[h][2], rb[h][3]);
+            da[0] = make_double2(va[0], va[1]); da[1] = make_double2(va[2], va[3]);
+            db[0] = make_double2(vb[0], vb[1]); db[1] = make_double2(vb[2], vb[3]);
         }
     };
 
@@ -307,6 +317,7 @@ int gram_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_
             if (eff > best + 0.01) { best = eff; splits = sp; }
         }
         int64_t rps = (n + splits - 1) / splits;
+        constexpr int DK = GramStage<T>::DK;
         rps = (rps + DK - 1) / DK * DK;
         splits = (n + rps - 1) / rps;
         const size_t smem = sizeof(double) * 4 * DK * DPITCH;
