@@ -226,7 +226,7 @@ def test_preprocess_kernels(torch):
 def test_savgol_and_outlier_filter(torch):
     """§8(f) f1 / f2: SNV + Savitzky-Golay derivative in one pass, PCA-Mahalanobis outlier cut."""
     rng = np.random.default_rng(4)
-    for p, win in ((700, 5), (1050, 15), (1024, 15), (256, 9), (128, 13), (16, 15), (64, 5), (33, 33)):
+    for p, win in ((700, 5), (1050, 15), (1024, 15), (256, 9), (128, 13), (16, 15), (64, 5), (33, 33), (2048, 11), (1156, 7)):
         X = synth.make_spectra(123, p, seed=p).astype(np.float32)
         ref = so.snv_savgol(X.astype(np.float64), window_length=win)
         got = engine.savgol(X, window_length=win, polyorder=2, deriv=1, snv=True).cpu().numpy()
@@ -446,6 +446,20 @@ def test_host_buffer_api(torch):
     np.testing.assert_allclose(Q, Qr, rtol=3e-5)
     assert_decisions(acc.astype(float), so.predict(ref, X.astype(np.float64)), so.reduced_distance(ref, T2r, Qr),
                      ref["D_limit"])
+    # the staging workspace is kept between calls: a larger chunk (workspace grows), the default chunk, rows with a
+    # leading dimension (2-D copy path) and a call after an explicit release must all give the same numbers
+    lib = native.lib()
+    Xp = np.zeros((5000, 1100), np.float32); Xp[:, :1024] = X
+    for Xa, ld, chunk in ((X, 1024, 4096), (X, 1024, 0), (Xp, 1100, 700)):
+        T2b = np.zeros(5000, np.float32); Qb = np.zeros(5000, np.float32); accb = np.zeros(5000, np.uint8)
+        native.check(lib.ocm_simca_score_host_f32(vp(Xa), 5000, 1024, ld, vp(mu), vp(P), vp(S), C.byref(prm), chunk,
+                                                  vp(T2b), vp(Qb), vp(accb)))
+        assert np.array_equal(T2b, T2) and np.array_equal(Qb, Q) and np.array_equal(accb, acc), (ld, chunk)
+    assert lib.ocm_simca_host_release() == 0
+    T2b = np.zeros(5000, np.float32)
+    native.check(lib.ocm_simca_score_host_f32(vp(X), 5000, 1024, 1024, vp(mu), vp(P), vp(S), C.byref(prm), 0, vp(T2b), None, None))
+    assert np.array_equal(T2b, T2)
+    assert lib.ocm_simca_host_release() == 0 and lib.ocm_simca_host_release() == 0
 
 
 def test_bad_arguments_raise(torch):
