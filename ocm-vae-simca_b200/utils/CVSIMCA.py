@@ -108,6 +108,8 @@ class _FoldModels:
     def __init__(self, Xd, y, splits, cls, A_max, need_train_scores):
         torch = engine._torch()
         self.folds = []
+        if not splits:                      # a rank without folds (more ranks than folds)
+            return
         row_sets = []
         for tr, te in splits:
             tr = np.asarray(tr)
@@ -130,8 +132,18 @@ class _FoldModels:
             self.folds.append(f)
 
 
-def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, store_predictions):
+def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, store_predictions, group=None):
+    """`group`: torch.distributed process group (or None).  With more than one rank the folds are dealt round-robin
+    (SURVEY.md §8(e)): every rank holds X, fits and scores only its folds, and the per-(fold, A) confusion counts and
+    the pooled decisions are summed over the ranks, so every rank returns the same table."""
     torch = engine._torch()
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as tdist
+        rank, world = tdist.get_rank(group), tdist.get_world_size(group)
+    n_folds = len(splits)
+    mine = [i for i in range(n_folds) if i % world == rank]
+    splits = [splits[i] for i in mine]
     base = clone(estimator)
     cls = base.model_class[0] if isinstance(base.model_class, (list, tuple, np.ndarray)) else base.model_class
     Xd = engine.to_device(X)
@@ -153,8 +165,8 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
         prm = eff_params(combo)
         cols = torch.as_tensor(np.asarray(lvs) - 1, device=Xd.device)
         pooled = torch.zeros((n_samples, len(lvs)), dtype=torch.uint8, device=Xd.device)
-        spec_folds = np.zeros((len(fm.folds), len(lvs)))
-        for fi, f in enumerate(fm.folds):
+        cnt_folds = torch.zeros((n_folds, len(lvs), 4), dtype=torch.int64, device=Xd.device)
+        for fi, f in zip(mine, fm.folds):
             # limits of every requested nested model of this fold (host scalars), then ONE launch
             # scores the fold's test rows and decides for all A at once
             ct = np.zeros(A_max, np.float32); cq = np.zeros(A_max, np.float32); dl = np.zeros(A_max, np.float32)
@@ -169,8 +181,15 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
                                             ct=ct, cq=cq, dlim=dl)
             acc = acc.index_select(1, cols).contiguous()
             pooled[f["te_idx"]] = acc
-            cnt = engine.conformity_counts(acc, f["is_target"]).cpu().numpy()
-            spec_folds[fi] = _percent_metrics(cnt[:, 0], cnt[:, 1], cnt[:, 2], cnt[:, 3])[1]
+            cnt_folds[fi] = engine.conformity_counts(acc, f["is_target"])
+        if world > 1:
+            pooled32 = pooled.to(torch.int32)                  # test rows are disjoint over folds: the sum is a merge
+            tdist.all_reduce(pooled32, group=group)
+            tdist.all_reduce(cnt_folds, group=group)
+            pooled = pooled32.to(torch.uint8)
+        cnt = cnt_folds.cpu().numpy()
+        spec_folds = np.stack([_percent_metrics(cnt[fi, :, 0], cnt[fi, :, 1], cnt[fi, :, 2], cnt[fi, :, 3])[1]
+                               for fi in range(n_folds)])
         cnt_all = engine.conformity_counts(pooled, tgt_all).cpu().numpy()
         sens_all, _ = _percent_metrics(cnt_all[:, 0], cnt_all[:, 1], cnt_all[:, 2], cnt_all[:, 3])
         pooled_h = pooled.cpu().numpy().astype(float) if store_predictions else None
@@ -189,12 +208,14 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
 # public entry point
 # ----------------------------------------------------------------------------------------------
 def cross_validate_simca_grid(estimator, X, y, cv, LV_min=2, LV_max=10, param_grid=None, refit_metric="eff",
-                              class_index=None, print_summary=True, store_predictions=False, batched="auto"):
+                              class_index=None, print_summary=True, store_predictions=False, batched="auto",
+                              group=None):
     """Grid x n-components x folds cross-validation of a SIMCA estimator (CVSIMCA.py:103-269).
 
     Returns {'results': [{params, LV, spec, sens, eff}], 'best_params', 'best_LV', 'best_score',
-    'best_estimator'[, 'by_combo']}.  `batched` ('auto' | True | False) selects the execution path;
-    it is the only argument the reference does not have."""
+    'best_estimator'[, 'by_combo']}.  Two arguments the reference does not have: `batched`
+    ('auto' | True | False) selects the execution path; `group` (a torch.distributed process group, batched path
+    only) deals the folds over the ranks -- every rank must make the same call and gets the same result."""
     if param_grid is None:
         param_grid = {}
     y = np.asarray(y)
@@ -222,7 +243,7 @@ def cross_validate_simca_grid(estimator, X, y, cv, LV_min=2, LV_max=10, param_gr
         else:
             combos, lv_of_combo = combos_full, [lv_values] * len(combos_full)
         results_records, by_combo_predictions = _run_batched(base_est, X, y, splits, combos, lv_of_combo,
-                                                             grid_includes_ncomp, store_predictions)
+                                                             grid_includes_ncomp, store_predictions, group)
     else:
         for combo in ParameterGrid(param_grid):
             for lv in ([None] if grid_includes_ncomp else lv_values):

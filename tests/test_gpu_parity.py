@@ -462,6 +462,19 @@ def test_host_buffer_api(torch):
     assert lib.ocm_simca_host_release() == 0 and lib.ocm_simca_host_release() == 0
 
 
+def test_cv_grid_folds_over_ranks(torch):
+    """§8(e): folds dealt over two ranks (gloo, both on this GPU) give the single-process CV table on every rank."""
+    import subprocess, sys, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OCM_DIST_BACKEND="gloo", OCM_CV_FULL="0")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "cv_dist_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == 2 and line["identical_on_all_ranks"]
+
+
 def test_bad_arguments_raise(torch):
     prm = native.ScoreParams(A=65, rule=1)
     rc = native.lib().ocm_simca_score_f32(None, 1, 8, 8, None, None, None, C.byref(prm), None, None, None, None, None)
