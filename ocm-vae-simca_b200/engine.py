@@ -359,9 +359,35 @@ def fit_pca_folds(X, row_sets, k) -> list:
     return models
 
 
-def fit_pca(X, row_idx=None, k=2, group=None) -> PCAModel:
+def _full_spectrum(Cm, n, p):
+    """All eigenvalues of the covariance, descending, as the reference keeps them (min(n, p) entries)."""
+    torch = _torch()
+    evals = torch.flip(torch.linalg.eigvalsh(Cm), dims=[-1])
+    m = min(n, p)
+    eigs = evals[:m].clamp_min(0.0).cpu().numpy()
+    if n <= p:
+        eigs[n - 1:] = 0.0     # rank n-1: the reference's trailing values are ~1e-30 noise
+    return eigs
+
+
+def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False) -> PCAModel:
+    """PCA of the selected rows: mean, k leading loadings (sign-normalised rows) and the eigenvalue spectrum.
+
+    Default: block subspace iteration for the k leading pairs + traces of the deflated covariance for the tail sums
+    (everything the limits need); `eigs_all` is then a `limits.LazySpectrum` that runs the full eigenvalue solve only
+    if the whole array is asked for.  `full_spectrum=True` (or a subspace iteration that did not converge: flat
+    spectrum at k) takes the full symmetric eigensolve straight away."""
+    from .limits import LazySpectrum
     Cm, mean, n = covariance(X, row_idx, group)
     p = X.shape[1]
+    if not full_spectrum and k < p:
+        w, V, tails, conv = eig_topk_subspace(Cm.unsqueeze(0), k, tol=1e-13, max_iter=90)
+        if bool(conv[0]):
+            P = V[0, :, :k].transpose(0, 1).contiguous()
+            sign_normalise_(P)
+            lam = np.maximum(w[0, :k].cpu().numpy(), 0.0)
+            spec = LazySpectrum(lam, np.maximum(tails[0].cpu().numpy(), 0.0), lambda: _full_spectrum(Cm, n, p))
+            return PCAModel(mean=mean, P=P, eigs_all=spec, n_samples=n)
     evals, evecs = eigh_topk(Cm, k)
     m = min(n, p)
     eigs = evals[:m].clamp_min(0.0).cpu().numpy()

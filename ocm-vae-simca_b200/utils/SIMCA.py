@@ -53,6 +53,39 @@ class _DevicePCA:
         return np.asarray(T) @ self.components_ + self.mean_
 
 
+class _ModelDict(dict):
+    """`_model[cls]` of the reference (SIMCA.py:83-99) with one lazy entry: 'eigs_all' holds the leading eigenvalues and
+    the tail power sums the limits were computed from, and turns into the full eigenvalue array (one extra symmetric
+    eigenvalue solve) the first time it is read."""
+
+    def _materialise(self):
+        v = dict.get(self, "eigs_all")
+        if hasattr(v, "full"):
+            dict.__setitem__(self, "eigs_all", v.full())
+
+    def __getitem__(self, key):
+        if key == "eigs_all":
+            self._materialise()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        if key == "eigs_all":
+            self._materialise()
+        return dict.get(self, key, default)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def copy(self):
+        self._materialise()
+        return _ModelDict(dict.copy(self))
+
+
 class SIMCA(BaseEstimator, ClassifierMixin):
     def __init__(self, n_components=2, model_class=None, type: str = 'alt', t2lim='Fdist', t2cl=0.95,
                  qlim='jm', qcl=0.95, dcl=0.95, maxPC=20, criteria='compl', verbose=True):
@@ -128,7 +161,7 @@ class SIMCA(BaseEstimator, ClassifierMixin):
             if self.qlim == 'chi2pom':
                 self._qdof, self._qscfact = lim.qdof, lim.qscale
             T2red, Qred = T2h / lim.T2_limit, Qh / lim.Q_limit
-        return {
+        return _ModelDict({
             "pca_model": _DevicePCA(pca),
             "n_components": A,
             "xmean": pca.mean.cpu().numpy(),
@@ -148,7 +181,7 @@ class SIMCA(BaseEstimator, ClassifierMixin):
             "_pca": pca,
             "_Sinv": Sinv,
             "_limits": lim,
-        }
+        })
 
     # ------------------------------------------------------------------ scoring ---------
     def _score_class(self, Xd, cls, snv=False):
