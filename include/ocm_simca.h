@@ -153,8 +153,6 @@ int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
 /* debugging aid: synchronises the device and returns 0 if no bounded mbarrier wait of the tcgen05
  * kernel ever timed out in this process, 1 if one did, -1 on a CUDA error */
 int ocm_simca_score_tc_status(void);
-/* bring-up aid: device buffer [128][1024] that receives the residual of tile 0 (NULL switches it off) */
-int ocm_simca_score_tc_debug(float* buf);
 
 /* ---- a12: all nested models A = 1..Amax in one pass (CV grid, CVSIMCA.py:157-200) ------
  * inv_eig[Amax] = 1/lambda_a (diagonal Sinv of a PCA model).  Outputs are [n][Amax]:

@@ -15,7 +15,7 @@
 // MN-major operand (reconstruction, K = components): for 16-bit types the K-major and MN-major 128B-swizzle
 // atoms are byte-identical, so ONE shared-memory copy of P (96 KB) serves both; kind::tf32 accepts MN-major
 // only in the 32B-base swizzle, which needs a second 128 KB copy that does not fit (found on the B200:
-// a plain MN-major tf32 descriptor is a silent no-op, tools/tc_diag.py).
+// a plain MN-major tf32 descriptor is a silent no-op).
 // The tensor core accumulates with truncation, so the large (1,1) products rotate over four accumulators
 // (16 chained accumulations each, bias < 1e-6).  A tcgen05.mma that accumulates into the SAME TMEM tile as its
 // predecessor waits for it (~100 cycles measured for these small N = 16 MMAs, which made the MMA warp the
@@ -96,8 +96,6 @@ constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
 
 __device__ unsigned int g_tc_timeout = 0;
-__device__ float* g_tc_debug = nullptr;      // optional [128][1024] dump of the residual of tile 0 (tests / bring-up)
-__device__ unsigned int g_tc_variant = 0;    // bring-up switches for the residual MMA (0 = production)
 
 // ---------------------------------------------------------------- PTX wrappers ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +140,21 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  The wait has no data
+// dependence on them, so the compiler is free to schedule ordinary arithmetic on those registers between the load and
+// the wait.  Passing the registers through an empty volatile asm AFTER the wait pins every later use behind it.
+__device__ __forceinline__ void tc_wait_ld16(uint32_t* v) {
+    tc_wait_ld();
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld16x2(uint32_t* a, uint32_t* b) {
+    tc_wait_ld();
+    asm volatile("" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                      "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]) :: "memory");
+    asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                      "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]) :: "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -272,7 +285,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
 }
 
-template <bool DEBUG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -441,7 +453,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                         uint32_t c0[16], c1[16];
                         tc_ld16(lane_addr + c0a, c0);
                         tc_ld16(lane_addr + c1a, c1);
-                        tc_wait_ld();
+                        tc_wait_ld16x2(c0, c1);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) cross[i] += __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
                     };
@@ -453,12 +465,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     uint32_t m0[16], m1[16];
                     tc_ld16(lane_addr + TM_D1 + 0u, m0);
                     tc_ld16(lane_addr + TM_D1 + 48u, m1);
-                    tc_wait_ld();
+                    tc_wait_ld16x2(m0, m1);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(m0[i]) + __uint_as_float(m1[i]);
                     tc_ld16(lane_addr + TM_D1 + 96u, m0);
                     tc_ld16(lane_addr + TM_D1 + 144u, m1);
-                    tc_wait_ld();
+                    tc_wait_ld16x2(m0, m1);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
                 }
@@ -508,7 +520,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     }
                     uint32_t v[QCOLS];
                     tc_ld16(dbase + (uint32_t)(sub * STAGE_COLS), v);
-                    tc_wait_ld();
+                    tc_wait_ld16(v);
                     if (sub == SUBS - 1) {
                         tc_fence_before();
                         mbar_arrive(BAR(B_DFREE) + 8u * b);                    // my part of the buffer is in registers
@@ -517,14 +529,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     for (int i = 0; i < QCOLS / 2; ++i) {
                         const f32x2 r = sub2(xc[i], pk2(v[2 * i], v[2 * i + 1]));
                         q2 = fma2(r, r, q2);
-                        if constexpr (DEBUG) {
-                            if (g_tc_debug != nullptr && blockIdx.x == 0 && k == 0) {       // residual of tile 0 (p <= 1024)
-                                uint32_t r0, r1;
-                                upk2(r, r0, r1);
-                                float* d = g_tc_debug + (size_t)row * 1024 + c2 * D2_COLS + sub * STAGE_COLS + QCOLS * qd + 2 * i;
-                                d[0] = __uint_as_float(r0); d[1] = __uint_as_float(r1);
-                            }
-                        }
                     }
                 }
             }
@@ -584,9 +588,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         constexpr uint32_t IDESC_N48 = make_idesc(TILE_M, 48, false, false);
         constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false);
         constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false);
-        const unsigned int variant = DEBUG ? g_tc_variant : 0u;
-        const uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, (variant & 1u) != 0, !(variant & 4u));
-        const uint32_t lbo2 = (variant & 2u) ? 1024u : (uint32_t)SM_PATOM, sbo2 = (variant & 2u) ? (uint32_t)SM_PATOM : 1024u;
+        constexpr uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, false, true);        // B = P read MN-major
+        constexpr uint32_t lbo2 = (uint32_t)SM_PATOM, sbo2 = 1024u;
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
@@ -647,8 +650,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     }
 }
 
-static bool h_debug_on = false;        // host mirrors of the bring-up hooks (no device read on the launch path)
-static unsigned int h_variant = 0;
 
 // ---- host side: TMA descriptor of the spectra matrix ---------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -711,24 +712,13 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     int rc = tc::make_tensor_map(&tmap, X, n, p, ldx);
     if (rc) return rc;
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
-    const bool debug = tc::h_debug_on || tc::h_variant != 0;  // bring-up only; the production kernel has neither hook
-    auto kern = debug ? tc::score_tc_kernel<true> : tc::score_tc_kernel<false>;
+    auto kern = tc::score_tc_kernel;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
     int64_t blocks = sm_count();
     if (blocks > ntiles) blocks = ntiles;
     kern<<<(unsigned)blocks, tc::NTHREADS, tc::SM_TOTAL, (cudaStream_t)stream>>>(tmap, a);
     return check_launch("score_tc_kernel");
-}
-
-// bring-up aid: device buffer [128][1024] that receives the residual tile 0 of the next launches (NULL = off)
-extern "C" int ocm_simca_score_tc_debug(float* buf) {
-    ocm::tc::h_debug_on = buf != nullptr;
-    return (int)cudaMemcpyToSymbol(ocm::tc::g_tc_debug, &buf, sizeof(buf));
-}
-extern "C" int ocm_simca_score_tc_variant(unsigned int v) {
-    ocm::tc::h_variant = v;
-    return (int)cudaMemcpyToSymbol(ocm::tc::g_tc_variant, &v, sizeof(v));
 }
 
 // 0 = no protocol timeout seen so far (synchronises the device; debugging / tests only)

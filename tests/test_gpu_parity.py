@@ -386,6 +386,33 @@ def test_tensor_core_kernel_matches_oracle(torch):
         assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
 
 
+def test_tensor_core_kernel_every_row_and_repeatable(torch):
+    """Every row of a 2 M-row launch against the FP32-pipe kernel (a pipeline race would show up as isolated bad rows),
+    bitwise identical results from launch to launch, no bounded wait timed out (tools/tc_stress.py does 10 M rows)."""
+    dev = torch.device("cuda"); lib = native.lib()
+    n, A, p = 2_000_000 + 77, 10, 1024
+    X = synth.make_spectra_device(n, p, dev, seed=3)
+    pca = engine.fit_pca(X[:5000].contiguous(), None, A)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev)).float().contiguous()
+    mu32, P32 = pca.arrays32()
+    prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
+    vp = lambda t: C.c_void_p(t.data_ptr()); st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(fn):
+        T2 = torch.empty(n, device=dev); Q = torch.empty(n, device=dev); acc = torch.empty(n, dtype=torch.uint8, device=dev)
+        native.check(fn(vp(X), n, p, p, vp(mu32), vp(P32), vp(Sinv), C.byref(prm), vp(T2), vp(Q), vp(acc), st))
+        torch.cuda.synchronize()
+        return T2, Q, acc
+    T2s, Qs, accs = run(lib.ocm_simca_score_rowteam_f32)
+    first = run(lib.ocm_simca_score_tc_f32)
+    assert float(((first[1] - Qs).abs() / Qs).max()) < 4e-5 and float(((first[0] - T2s).abs() / T2s.clamp_min(1e-6)).max()) < 4e-5
+    assert int((first[2] != accs).sum()) <= 3                       # rows within rounding of the critical distance
+    for _ in range(3):
+        again = run(lib.ocm_simca_score_tc_f32)
+        assert all(torch.equal(a, b) for a, b in zip(first, again))
+    assert lib.ocm_simca_score_tc_status() == 0
+
+
 def test_nonfinite_rows_are_rejected_and_isolated(torch):
     """The reference's drivers drop NaN / inf spectra before SIMCA (simca_nuts.py:55-66); if one slips through, numpy
     gives NaN distances and `NaN < limit` is False.  Every kernel must do the same and must not let a bad row touch
