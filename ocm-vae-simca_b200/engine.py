@@ -88,6 +88,7 @@ def snv(X, eps=1e-8):
 
 
 _SG_CACHE = {}
+_SG_DEVICE = {}      # (window, order, deriv, delta, device) -> (host taps, device edge matrices)
 
 
 def _savgol_tables(window, polyorder, deriv, delta):
@@ -113,9 +114,11 @@ def savgol(X, window_length=5, polyorder=2, deriv=1, delta=1.0, snv=False, snv_e
     X = to_device(X, dtype=torch.float32)
     if out is None:
         out = torch.empty_like(X)
-    g, el, er = _savgol_tables(int(window_length), int(polyorder), int(deriv), delta)
-    el_d = torch.as_tensor(el, device=X.device).contiguous()
-    er_d = torch.as_tensor(er, device=X.device).contiguous()
+    key = (int(window_length), int(polyorder), int(deriv), float(delta), str(X.device))
+    if key not in _SG_DEVICE:
+        g, el, er = _savgol_tables(int(window_length), int(polyorder), int(deriv), delta)
+        _SG_DEVICE[key] = (g, torch.as_tensor(el, device=X.device).contiguous(), torch.as_tensor(er, device=X.device).contiguous())
+    g, el_d, er_d = _SG_DEVICE[key]
     rc = native.lib().ocm_savgol_f32(_p(X), X.shape[0], X.shape[1], X.stride(0), int(bool(snv)), float(snv_eps),
                                      g.ctypes.data_as(C.c_void_p), int(window_length), _p(el_d), _p(er_d), _p(out),
                                      out.stride(0), _stream())
@@ -218,23 +221,11 @@ def sign_normalise_(V):
 
 
 def eigh_topk(Cm, k):
-    """All eigenvalues (descending) and the k leading eigenvectors (rows) of a symmetric fp64
-    matrix, on the device."""
+    """All eigenvalues (descending) and the k leading eigenvectors (rows) of a symmetric fp64 matrix, on the device
+    (cuSOLVER through torch.linalg.eigh).  Only the full-spectrum path uses it: a fit that asks for `full_spectrum`,
+    a subspace iteration that did not converge; the default fit and the CV folds use eig_topk_subspace."""
     torch = _torch()
-    lib = native.lib()
-    if hasattr(lib, "ocm_eigh_topk_f64") and getattr(lib.ocm_eigh_topk_f64, "argtypes", None):
-        p = Cm.shape[-1]
-        batch = 1 if Cm.dim() == 2 else Cm.shape[0]
-        evals = torch.empty((batch, p), dtype=torch.float64, device=Cm.device)
-        evecs = torch.empty((batch, k, p), dtype=torch.float64, device=Cm.device)
-        wb = int(lib.ocm_eigh_work_bytes(p, k, batch))
-        work = torch.empty(wb, dtype=torch.uint8, device=Cm.device)
-        A = Cm.clone()
-        native.check(lib.ocm_eigh_topk_f64(_p(A), p, k, batch, _p(evals), _p(evecs), _p(work), wb, _stream()),
-                     "ocm_eigh_topk_f64")
-        if Cm.dim() == 2:
-            return evals[0], evecs[0]
-        return evals, evecs
+    native.require_cuda()
     w, V = torch.linalg.eigh(Cm)
     w = torch.flip(w, dims=[-1])
     V = torch.flip(V, dims=[-1])[..., :k].transpose(-1, -2).contiguous()
