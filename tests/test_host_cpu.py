@@ -99,6 +99,50 @@ def test_limits_match_reference_golden(golden_dir):
                                    err_msg=str(name))
 
 
+def test_limits_property_random_spectra():
+    """Host limit arithmetic against the oracle's restatement of SIMCA.py:156-236 on random spectra / distances, and
+    the partial-spectrum form (leading values + tail power sums, what the partial eigensolve provides) against the
+    full eigenvalue array."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 12), st.integers(30, 400), st.integers(0, 10_000), st.floats(0.80, 0.999),
+           st.sampled_from(["sim", "alt", "ci", "dd"]), st.sampled_from(["Fdist", "Fdistrig", "chi2", "chi2pom", "perc"]),
+           st.sampled_from(["jm", "chi2box", "chi2pom", "perc"]))
+    def check(A, n, seed, cl, kind, t2l, ql):
+        rng = np.random.default_rng(seed)
+        eigs = np.sort(rng.gamma(1.0, 1.0, size=A + 25) * 0.7 ** np.arange(A + 25))[::-1].copy()
+        T2 = rng.chisquare(A, size=n) * 1.1
+        Q = rng.chisquare(6, size=n) * eigs[A:].sum() / 6
+        if kind == "dd":
+            t2l = ql = "chi2pom"
+        tl, tdof, tsc = so.t2_limit(T2, A, t2l, cl)
+        qlm, qdof, qsc = so.q_limit(Q, eigs, A, ql, cl)
+        dl = so.d_limit(kind, A, tl, qlm, eigs, cl, tdof, qdof)
+        lim = limits.all_limits(kind, t2l, cl, ql, cl, cl, A, n, eigs, T2, Q)
+        np.testing.assert_allclose([lim.T2_limit, lim.Q_limit, lim.D_limit], [tl, qlm, dl], rtol=1e-10)
+        tail = eigs[A + 3:]
+        part = limits.Spectrum(eigs[:A + 3], (tail.sum(), (tail ** 2).sum(), (tail ** 3).sum()))
+        lim2 = limits.all_limits(kind, t2l, cl, ql, cl, cl, A, n, part, T2, Q)
+        np.testing.assert_allclose([lim2.T2_limit, lim2.Q_limit, lim2.D_limit], [tl, qlm, dl], rtol=1e-9)
+    check()
+
+
+def test_lazy_spectrum_and_model_dict():
+    """`_model[cls]['eigs_all']` turns into the full eigenvalue array on first read, exactly once."""
+    from ocm_vae_simca_b200.utils.SIMCA import _ModelDict
+    calls = []
+    full = np.array([5.0, 3.0, 1.0, 0.5, 0.2])
+    sp = limits.LazySpectrum(full[:2], (full[2:].sum(), (full[2:] ** 2).sum(), (full[2:] ** 3).sum()),
+                             lambda: (calls.append(1), full)[1])
+    assert limits.tail_moments(sp, 1) == pytest.approx(limits.tail_moments(full, 1)) and not calls
+    d = _ModelDict({"eigs_all": sp, "D_limit": 1.0})
+    assert d["D_limit"] == 1.0 and not calls
+    assert isinstance(d["eigs_all"], np.ndarray) and d["eigs_all"].shape == (5,) and len(calls) == 1
+    assert np.array_equal(d.get("eigs_all"), full) and np.array_equal(dict(d.items())["eigs_all"], full) and len(calls) == 1
+    assert np.array_equal(np.asarray(sp), full)
+
+
 def test_shard_rows_partition():
     for n, w in [(10, 3), (7, 8), (10_000_000, 8), (0, 2)]:
         spans = [odist.shard_rows(n, r, w) for r in range(w)]
