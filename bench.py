@@ -23,6 +23,14 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every worker unless the user set it.  Rank 0 also times the CPU arms (the
+# reference's numpy / OpenBLAS arithmetic "with all the host threads it can use"), and OpenBLAS sizes its pool when numpy
+# is imported -- so rank 0 gets the cores back BEFORE that import.  The other ranks keep torchrun's setting.
+if os.environ.get("TORCHELASTIC_RUN_ID") and os.environ.get("RANK", "0") == "0":
+    _n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_n)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -119,6 +127,20 @@ def fit_bench_model_gpu(p, A, device):
     return pca, lim
 
 
+def _all_cores():
+    """BLAS / OpenMP pools opened to every host core for the CPU arms (torchrun exports OMP_NUM_THREADS=1, which would
+    silently time a one-thread baseline).  Returns (context manager, number of threads the BLAS pools will use)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        ctx = threadpool_limits(limits=n)
+        used = max([int(i.get("num_threads", 1)) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+        return ctx, used                      # what the BLAS pool really has after the request
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext(), int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def reference_arm(args, rank):
     """CPU arm: the oracle's restatement of SIMCA.predict (numpy/sklearn, all host threads) on a
     bounded sample of the same workload.  Rank 0 only."""
@@ -131,20 +153,22 @@ def reference_arm(args, rank):
     Xfit = synth.make_spectra(5000, p, seed=99).astype(np.float32)
     model = so.fit_one_class(Xfit.astype(np.float64), A, faithful_solver=True)
     X = synth.make_spectra(rows, p, seed=123).astype(np.float32)
-    for _ in range(max(args.warmup, 1)):
-        so.predict(model, X[: min(rows, 20000)])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        so.predict(model, X)
-    dt = time.perf_counter() - t0
+    pool, cores = _all_cores()
+    with pool:
+        for _ in range(max(args.warmup, 1)):
+            so.predict(model, X[: min(rows, 20000)])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            so.predict(model, X)
+        dt = time.perf_counter() - t0
     val = rows * args.steps / dt
     line = {
         "impl": "reference", "metric": "spectra scored/s (fused T2+Q)", "value": val, "unit": "spectra/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "spectra/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{rows} x {p} fp32 rows per step, oracle.simca_oracle.predict (numpy/OpenBLAS)"},
+        "cpu_baseline": {"value": val, "unit": "spectra/s", "cores": cores, "kind": "port",
+                         "sample": f"{rows} x {p} fp32 rows per step, oracle.simca_oracle.predict (numpy/OpenBLAS, {cores} threads)"},
         "e2e": {"value": val, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -165,14 +189,16 @@ def cpu_baseline_leg(args):
     Xfit = synth.make_spectra(5000, p, seed=99)
     model = so.fit_one_class(Xfit, A, faithful_solver=True)
     X = synth.make_spectra(rows, p, seed=123).astype(np.float32)
-    so.predict(model, X[:20000])
-    best = float("inf")
-    for _ in range(3):
-        t0 = time.perf_counter()
-        so.predict(model, X)
-        best = min(best, time.perf_counter() - t0)
-    return {"value": rows / best, "unit": "spectra/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{rows} x {p} fp32 rows, best of 3, oracle.simca_oracle.predict (numpy/OpenBLAS threads = all cores)"}
+    pool, cores = _all_cores()
+    with pool:
+        so.predict(model, X[:20000])
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            so.predict(model, X)
+            best = min(best, time.perf_counter() - t0)
+    return {"value": rows / best, "unit": "spectra/s", "cores": cores, "kind": "port",
+            "sample": f"{rows} x {p} fp32 rows, best of 3, oracle.simca_oracle.predict (numpy/OpenBLAS, {cores} threads)"}
 
 
 def cv_leg(device, group=None, rank=0, world=1):
@@ -214,14 +240,16 @@ def cv_leg(device, group=None, rank=0, world=1):
         from oracle import simca_oracle as so
         tr, te = next(iter(cv.split()))
         Xtr = X[tr][y[tr] == 0]
-        t0 = time.perf_counter()
-        cells = 0
-        for A in (5, 10, 15):
-            m = so.fit_one_class(Xtr, A, faithful_solver=True)
-            so.predict(m, X[te])
-            cells += 1
-        cdt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": cells / cdt, "unit": "fits/s", "cores": os.cpu_count(), "kind": "port",
+        pool, cores = _all_cores()
+        with pool:
+            t0 = time.perf_counter()
+            cells = 0
+            for A in (5, 10, 15):
+                m = so.fit_one_class(Xtr, A, faithful_solver=True)
+                so.predict(m, X[te])
+                cells += 1
+            cdt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": cells / cdt, "unit": "fits/s", "cores": cores, "kind": "port",
                                "sample": "3 (fold, A) cells of the same grid: oracle fit_one_class + predict"}
     except Exception as e:  # the oracle is a checker; its absence must not kill the GPU line
         out["cpu_baseline"] = {"error": repr(e)}
