@@ -75,14 +75,42 @@ int ocm_colstats_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_
 int ocm_colstats_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                      const double* shift, double* colsum, double* colsumsq, void* stream);
 
+/* One pass for the bulk fit: colsum[j] += sum_r x[r][j] (fp64), colmin[j] = min(colmin[j], min_r x[r][j]),
+ * colmax[j] likewise (fp32, rounded outwards for fp64 rows).  The caller initialises colmin to +inf and colmax
+ * to -inf; either may be NULL. */
+int ocm_colstats_minmax_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                            double* colsum, float* colmin, float* colmax, void* stream);
+int ocm_colstats_minmax_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                            double* colsum, float* colmin, float* colmax, void* stream);
+
 /* ---- a4: partitioned Gram accumulation (replaces the SVD inside sklearn PCA.fit,
  * utils/SIMCA.py:64-66,:75) ------------------------------------------------------------
  * G[i][j] += sum_r (x[r][i]-shift[i]) (x[r][j]-shift[j]) for j >= i (UPPER triangle only),
- * fp64 accumulation on the FP64 pipe.  G is p x p row-major with leading dimension p. */
+ * fp64 accumulation on the FP64 tensor pipe (DMMA; FP64 CUDA cores for tiny problems).
+ * G is p x p row-major with leading dimension p. */
 int ocm_gram_f64acc_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                         const double* shift, double* G, void* stream);
 int ocm_gram_f64acc_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                         const double* shift, double* G, void* stream);
+
+/* ---- a4, bulk: the same Gram on the 5th-generation tensor cores, exact integer arithmetic (csrc/gram_tc.cu).
+ * Rows are quantised to 31-bit fixed point per column, q = rint((x - shift) 2^sc) 2^-sc with 2^sc chosen from
+ * colmin / colmax (|q 2^sc| <= 2^30), split into four balanced int8 digit planes and contracted with
+ * tcgen05.mma.kind::i8 (int32 accumulators in TMEM, chains <= 32 704 rows, flushed into fp64):
+ *   G[i][j]   += sum_r q[r][i] q[r][j]   (j >= i, UPPER triangle only)
+ *   colsum[j] += sum_r q[r][j]           (exact: int64 accumulation; may be NULL)
+ * products = 16: every digit product -> the exact Gram of the quantised rows; 13: products of weight < 256^2
+ * dropped (<= 2^-37 max_i max_j per row); 10: weight < 256^3 dropped (<= 2^-28).
+ * colmin / colmax [p] fp32 bound the column values (ocm_colstats_minmax_*); flags [2] int64 (device, may be NULL)
+ * receives {values clamped because they exceeded the bounds, non-finite inputs} -- both must be 0 for the result to
+ * hold.  work: device scratch of ocm_gram_tc_workspace_bytes(n, p) bytes, 1024-byte aligned. */
+int ocm_gram_tc_workspace_bytes(int64_t n, int32_t p, int64_t* bytes);
+int ocm_gram_tc_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                    const double* shift, const float* colmin, const float* colmax, int32_t products,
+                    void* work, int64_t work_bytes, double* G, double* colsum, int64_t* flags, void* stream);
+int ocm_gram_tc_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                    const double* shift, const float* colmin, const float* colmax, int32_t products,
+                    void* work, int64_t work_bytes, double* G, double* colsum, int64_t* flags, void* stream);
 
 /* Combine per-partition moments into a covariance:  with weights w[g] in {0,1,...}
  *   N = sum w_g n_g,  s = sum w_g colsum_g,  G = sum w_g G_g,  d = s/N,

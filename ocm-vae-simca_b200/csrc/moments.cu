@@ -1,12 +1,11 @@
-// PCA-fit moments: column sums and the X^T X Gram of selected rows,
-// accumulated in fp64 on the FP64 pipe, plus the combination of per-partition moments
-// into a covariance.  This replaces the LAPACK SVD that sklearn's PCA runs inside
+// PCA-fit moments: column sums / extrema and the X^T X Gram of selected rows,
+// accumulated in fp64 (FP64 CUDA cores for tiny problems, the FP64 tensor pipe -- DMMA -- otherwise),
+// plus the combination of per-partition moments into a covariance.  This replaces the LAPACK SVD that sklearn's PCA runs inside
 // utils/SIMCA.py:64-66 / :75 -- the eigen-decomposition of the covariance gives the same
 // loadings and explained variances (S^2/(n-1)) without ever forming U.
 //
-// This is the exact path used for fits that fit in L2 (CV folds, config 1/2) where
-// accuracy, not throughput, is the constraint; the bulk config-4 path is the tensor-core
-// Gram in gram_tc.cu.  Rows are selected through an optional int64 gather index so CV
+// This is the path for fits that live in L2 (CV folds, config 1/2) and the checker of the
+// bulk config-4 path, the integer tcgen05 Gram in gram_tc.cu.  Rows are selected through an optional int64 gather index so CV
 // folds never materialise copies of X.
 #include "ocm_common.cuh"
 
@@ -33,6 +32,97 @@ colstats_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict_
     }
     atomicAdd(colsum + j, s);
     if (colsumsq) atomicAdd(colsumsq + j, ss);
+}
+
+// ---------------------------------------------------------------- column sums + extrema --
+// One pass for the bulk fit: sum (fp64), min and max (fp32 bit patterns, see atomic_min/max_float) of every column.
+// Thread -> 4 consecutive columns (128-bit loads when aligned), rows strided over gridDim.y, 4 rows in flight.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ float to_float_up(float v) { return v; }
+__device__ __forceinline__ float to_float_dn(float v) { return v; }
+__device__ __forceinline__ float to_float_up(double v) { return __double2float_ru(v); }
+__device__ __forceinline__ float to_float_dn(double v) { return __double2float_rd(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colstats_minmax_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx, int64_t n, int p,
+                       double* __restrict__ colsum, float* __restrict__ colmin, float* __restrict__ colmax, int vec_ok) {
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= p) return;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    T mn[4], mx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { mn[e] = (T)INFINITY; mx[e] = (T)-INFINITY; }
+    const bool full = j0 + 3 < p;
+    auto load = [&](int64_t r, T* v) {
+        const int64_t row = row_idx ? row_idx[r] : r;
+        const T* xr = X + row * ldx + j0;
+        if constexpr (sizeof(T) == 4) {
+            if (vec_ok && full) {
+                const float4 t = ldg_stream4(reinterpret_cast<const float*>(xr));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                return;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (j0 + e < p) ? xr[e] : T(0);
+    };
+    const int64_t step = gridDim.y;
+    int64_t r = blockIdx.y;
+    for (; r + 3 * step < n; r += 4 * step) {
+        T v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load(r + u * step, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s[e] += (double)v[u][e];
+                mn[e] = v[u][e] < mn[e] ? v[u][e] : mn[e];
+                mx[e] = v[u][e] > mx[e] ? v[u][e] : mx[e];
+            }
+    }
+    for (; r < n; r += step) {
+        T v[4];
+        load(r, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            s[e] += (double)v[e];
+            mn[e] = v[e] < mn[e] ? v[e] : mn[e];
+            mx[e] = v[e] > mx[e] ? v[e] : mx[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (j0 + e >= p) break;
+        atomicAdd(colsum + j0 + e, s[e]);
+        if (colmin) atomic_min_float(colmin + j0 + e, to_float_dn(mn[e]));
+        if (colmax) atomic_max_float(colmax + j0 + e, to_float_up(mx[e]));
+    }
+}
+
+template <typename T>
+int colstats_minmax_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p, double* colsum,
+                         float* colmin, float* colmax, void* stream) {
+    if (n == 0) return 0;
+    OCM_REQUIRE(X && colsum && n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
+    const int threads = 256, cols_per_block = threads * 4;
+    const int gx = (p + cols_per_block - 1) / cols_per_block;
+    int64_t gy = (int64_t)sm_count() * 8 / gx;
+    if (gy > (n + 7) / 8) gy = (n + 7) / 8;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    const int vec_ok = (sizeof(T) == 4 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) ? 1 : 0;
+    dim3 grid(gx, (unsigned)gy);
+    colstats_minmax_kernel<T><<<grid, threads, 0, (cudaStream_t)stream>>>(X, ldx, row_idx, n, p, colsum, colmin, colmax, vec_ok);
+    return check_launch("colstats_minmax_kernel");
 }
 
 // ---------------------------------------------------------------- fp64 Gram -------------
@@ -353,6 +443,14 @@ extern "C" int ocm_colstats_f32(const float* X, int64_t ldx, const int64_t* row_
 extern "C" int ocm_colstats_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                                 const double* shift, double* colsum, double* colsumsq, void* stream) {
     return ocm::colstats_impl<double>(X, ldx, row_idx, n, p, shift, colsum, colsumsq, stream);
+}
+extern "C" int ocm_colstats_minmax_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                       double* colsum, float* colmin, float* colmax, void* stream) {
+    return ocm::colstats_minmax_impl<float>(X, ldx, row_idx, n, p, colsum, colmin, colmax, stream);
+}
+extern "C" int ocm_colstats_minmax_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
+                                       double* colsum, float* colmin, float* colmax, void* stream) {
+    return ocm::colstats_minmax_impl<double>(X, ldx, row_idx, n, p, colsum, colmin, colmax, stream);
 }
 extern "C" int ocm_gram_f64acc_f32(const float* X, int64_t ldx, const int64_t* row_idx, int64_t n, int32_t p,
                                    const double* shift, double* G, void* stream) {

@@ -157,6 +157,54 @@ def colstats(X, row_idx=None, shift=None, want_sq=False):
     return s, ss, n
 
 
+def colstats_minmax(X, row_idx=None):
+    """One pass: column sums (fp64) and column extrema (fp32, rounded outwards) of the selected rows."""
+    torch = _torch()
+    n = X.shape[0] if row_idx is None else row_idx.numel()
+    p = X.shape[1]
+    s = torch.zeros(p, dtype=torch.float64, device=X.device)
+    mn = torch.full((p,), float("inf"), dtype=torch.float32, device=X.device)
+    mx = torch.full((p,), float("-inf"), dtype=torch.float32, device=X.device)
+    fn = native.lib().ocm_colstats_minmax_f32 if X.dtype == torch.float32 else native.lib().ocm_colstats_minmax_f64
+    native.check(fn(_p(X), X.stride(0), _p(row_idx), n, p, _p(s), _p(mn), _p(mx), _stream()), "ocm_colstats_minmax")
+    return s, mn, mx, n
+
+
+_GRAM_TC_WS = {}     # device index -> uint8 tensor (grown on demand)
+
+
+def _gram_tc_workspace(n, p, device):
+    torch = _torch()
+    need = C.c_int64(0)
+    native.check(native.lib().ocm_gram_tc_workspace_bytes(int(n), int(p), C.byref(need)), "ocm_gram_tc_workspace_bytes")
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _GRAM_TC_WS.get(key)
+    if ws is None or ws.numel() < need.value + 1024:
+        _GRAM_TC_WS[key] = ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=device)
+    off = (-ws.data_ptr()) % 1024
+    return ws, off, need.value
+
+
+def gram_tc(X, row_idx, shift, colmin, colmax, products=13, out=None, colsum=None):
+    """Upper triangle of the Gram of the quantised shifted rows on the integer tensor cores (ocm_gram_tc_*), plus the
+    exact column sums of the same quantised rows.  Returns (G [p,p] f64, colsum [p] f64, flags [2] int64 on the device:
+    clamped values, non-finite inputs)."""
+    torch = _torch()
+    n = X.shape[0] if row_idx is None else row_idx.numel()
+    p = X.shape[1]
+    if out is None:
+        out = torch.zeros((p, p), dtype=torch.float64, device=X.device)
+    if colsum is None:
+        colsum = torch.zeros(p, dtype=torch.float64, device=X.device)
+    flags = torch.zeros(2, dtype=torch.int64, device=X.device)
+    ws, off, nbytes = _gram_tc_workspace(n, p, X.device)
+    fn = native.lib().ocm_gram_tc_f32 if X.dtype == torch.float32 else native.lib().ocm_gram_tc_f64
+    rc = fn(_p(X), X.stride(0), _p(row_idx), n, p, _p(shift), _p(colmin), _p(colmax), int(products),
+            C.c_void_p(ws.data_ptr() + off), nbytes, _p(out), _p(colsum), _p(flags), _stream())
+    native.check(rc, "ocm_gram_tc")
+    return out, colsum, flags
+
+
 def gram(X, row_idx=None, shift=None, out=None):
     """Upper triangle of sum_r (x_r - shift)(x_r - shift)^T, fp64 accumulation."""
     torch = _torch()

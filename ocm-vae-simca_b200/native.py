@@ -94,6 +94,11 @@ SIGNATURES = {
     "ocm_savgol_f32": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "ocm_colstats_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ocm_colstats_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "ocm_colstats_minmax_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "ocm_colstats_minmax_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "ocm_gram_tc_workspace_bytes": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
+    "ocm_gram_tc_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ocm_gram_tc_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ocm_gram_f64acc_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ocm_gram_f64acc_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ocm_cov_from_parts_f64": (C.c_int, [_vp, _vp, C.POINTER(_i64), C.POINTER(C.c_double), _i32, _i32,
