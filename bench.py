@@ -10,8 +10,13 @@ every step streams from HBM; no explicit L2 flush is needed).
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
   python bench.py --impl reference ...                           # CPU oracle arm (reference algorithm)
 
-Extra keys beyond the base contract: `roofline`, `cpu_baseline`, `e2e`, `clocks`,
-`gpu_launches`, and `cv` (BASELINE.json's second metric: CVSIMCA fits/s on configs[1]).
+Extra keys beyond the base contract: `roofline`, `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, and the legs
+  `strong` -- the same 10 M rows in TOTAL split over the N GPUs (configs[2] read as strong scaling),
+  `fit`    -- BASELINE configs[3]: row-sharded PCA fit (column statistics, integer tcgen05 Gram, NCCL all-reduce of the
+              partial moments, eigensolve) at 2 M x 2048 rows per GPU, tensor roofline,
+  `cv`     -- BASELINE.json's second metric: CVSIMCA fits/s on configs[1].
+The CPU arms time the UNMODIFIED reference staged in baseline/_ref (kind "reference"); when that directory is absent
+(nothing staged) they fall back to the oracle's restatement (kind "port").
 """
 from __future__ import annotations
 
@@ -51,6 +56,10 @@ def parse():
     ap.add_argument("--A", type=int, default=10)
     ap.add_argument("--e2e-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-rows", type=int, default=200_000)
+    ap.add_argument("--fit-rows", type=int, default=2_000_000, help="rows per GPU of the PCA-fit leg")
+    ap.add_argument("--fit-p", type=int, default=2048)
+    ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-cv", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -66,6 +75,54 @@ def measured_peak():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained / bf16_tflops)"
+    except Exception:
+        return 1400.0, 1590.0, "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained)"
+
+
+def reference_modules():
+    """The unmodified reference staged in baseline/_ref, or None (then the oracle port is timed)."""
+    try:
+        from baseline import ref_loader
+        if ref_loader.available():
+            return ref_loader.load()
+    except Exception:
+        pass
+    return None
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE the pinned staging buffers are
+    allocated (first touch puts their pages on that node).  Returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(index), "pci_device_id", 0)
+        if bus is None:
+            return {"numa": "unknown (no pci id)"}
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa": "single node / not reported"}
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:
+        return {"numa": f"not bound ({type(e).__name__})"}
 
 
 class ClockSampler:
@@ -141,25 +198,45 @@ def _all_cores():
         return contextlib.nullcontext(), int(os.environ.get("OMP_NUM_THREADS", n))
 
 
+def _cpu_predict_runner(args):
+    """Returns (predict(X) -> decisions, kind, description): the staged reference's own SIMCA.fit / predict
+    (utils/SIMCA.py), else the oracle port.  fp32 rows, as in the GPU workload."""
+    from ocm_vae_simca_b200 import synth
+    p, A = args.p, args.A
+    Xfit = synth.make_spectra(5000, p, seed=99).astype(np.float32)
+    ref = reference_modules()
+    if ref is not None:
+        import contextlib, io
+        np.random.seed(0)                      # the reference's second PCA is an unseeded randomized SVD
+        m = ref[0].SIMCA(n_components=A, model_class=0, verbose=False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.fit(Xfit, np.zeros(Xfit.shape[0], dtype=np.int64))
+
+        def run(X):
+            with contextlib.redirect_stdout(io.StringIO()):
+                return m.predict(X)
+        return run, "reference", "baseline/_ref utils/SIMCA.py SIMCA.predict (unmodified reference, numpy/sklearn/OpenBLAS)"
+    from oracle import simca_oracle as so
+    model = so.fit_one_class(Xfit.astype(np.float64), A, faithful_solver=True)
+    return (lambda X: so.predict(model, X)), "port", "oracle.simca_oracle.predict (restatement; baseline/_ref not staged)"
+
+
 def reference_arm(args, rank):
-    """CPU arm: the oracle's restatement of SIMCA.predict (numpy/sklearn, all host threads) on a
-    bounded sample of the same workload.  Rank 0 only."""
+    """CPU arm: the reference's own SIMCA.predict on the box's host cores (all threads), on a bounded sample of the
+    same workload per step.  Rank 0 only."""
     if rank != 0:
         return
     from ocm_vae_simca_b200 import synth
-    from oracle import simca_oracle as so
-    p, A = args.p, args.A
-    rows = args.cpu_rows
-    Xfit = synth.make_spectra(5000, p, seed=99).astype(np.float32)
-    model = so.fit_one_class(Xfit.astype(np.float64), A, faithful_solver=True)
+    p, rows = args.p, args.cpu_rows
+    run, kind, what = _cpu_predict_runner(args)
     X = synth.make_spectra(rows, p, seed=123).astype(np.float32)
     pool, cores = _all_cores()
     with pool:
         for _ in range(max(args.warmup, 1)):
-            so.predict(model, X[: min(rows, 20000)])
+            run(X[: min(rows, 20000)])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            so.predict(model, X)
+            run(X)
         dt = time.perf_counter() - t0
     val = rows * args.steps / dt
     line = {
@@ -167,8 +244,8 @@ def reference_arm(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "spectra/s", "cores": cores, "kind": "port",
-                         "sample": f"{rows} x {p} fp32 rows per step, oracle.simca_oracle.predict (numpy/OpenBLAS, {cores} threads)"},
+        "cpu_baseline": {"value": val, "unit": "spectra/s", "cores": cores, "kind": kind,
+                         "sample": f"{rows} x {p} fp32 rows per step, {what}, {cores} threads"},
         "e2e": {"value": val, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -184,21 +261,93 @@ def workload_config(args):
 
 def cpu_baseline_leg(args):
     from ocm_vae_simca_b200 import synth
-    from oracle import simca_oracle as so
-    p, A, rows = args.p, args.A, args.cpu_rows
-    Xfit = synth.make_spectra(5000, p, seed=99)
-    model = so.fit_one_class(Xfit, A, faithful_solver=True)
+    p, rows = args.p, args.cpu_rows
+    run, kind, what = _cpu_predict_runner(args)
     X = synth.make_spectra(rows, p, seed=123).astype(np.float32)
     pool, cores = _all_cores()
     with pool:
-        so.predict(model, X[:20000])
+        run(X[:20000])
         best = float("inf")
         for _ in range(3):
             t0 = time.perf_counter()
-            so.predict(model, X)
+            run(X)
             best = min(best, time.perf_counter() - t0)
-    return {"value": rows / best, "unit": "spectra/s", "cores": cores, "kind": "port",
-            "sample": f"{rows} x {p} fp32 rows, best of 3, oracle.simca_oracle.predict (numpy/OpenBLAS, {cores} threads)"}
+    return {"value": rows / best, "unit": "spectra/s", "cores": cores, "kind": kind,
+            "sample": f"{rows} x {p} fp32 rows, best of 3, {what}, {cores} threads"}
+
+
+def fit_leg(args, device, group, rank, world):
+    """BASELINE configs[3] per GPU: rows sharded, partial {Gram, sums, count} all-reduced (NCCL), eigensolve on every
+    rank.  Device-timed phases (CUDA events), max over ranks of the total."""
+    import torch
+    from ocm_vae_simca_b200 import dist as odist
+    from ocm_vae_simca_b200 import engine, native, synth
+    rows, p, k = args.fit_rows, args.fit_p, 20
+    X = torch.empty((rows, p), dtype=torch.float32, device=device)
+    synth.make_spectra_device(rows, p, device, seed=2000 + rank, out=X)
+    engine.fit_pca(X, None, k, group=group)                     # warm-up (workspace, NCCL channels, cuTensorMap encoder)
+    engine.fit_pca(X, None, k, group=group)
+    torch.cuda.synchronize()
+    if group is not None:
+        import torch.distributed as dist
+        dist.barrier()
+    reps, totals, phases = 3, [], None
+    l0 = native.launch_count()
+    for _ in range(reps):
+        tm = engine.PhaseTimer()
+        pca = engine.fit_pca(X, None, k, group=group, timer=tm)
+        ph = tm.result()
+        totals.append(sum(ph.values()))
+        if phases is None or totals[-1] == min(totals):
+            phases = ph
+    launches = (native.launch_count() - l0) // reps
+    total_ms = odist.max_over_ranks(min(totals), device)
+    gram_ms = odist.max_over_ranks(phases.get("gram", float("nan")), device)
+    del X
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    sus, burst, src = measured_tensor_peak()
+    flop = rows * p * (p + 1.0)                                  # SURVEY.md §8(d): symmetric rank-k update, per GPU
+    achieved = flop / (gram_ms * 1e-3) / 1e12
+    out = {"metric": "PCA fit rows/s (Gram + all-reduce + eigensolve)", "value": world * rows / (total_ms * 1e-3), "unit": "rows/s",
+           "n_gpus": world, "rows_per_gpu": rows, "p": p, "n_components": k, "scaling": "weak",
+           "ms": {"total_max_over_ranks": total_ms, **{k_: round(v, 3) for k_, v in phases.items()}},
+           "gram": {"kernel": "gtc::gram_tc_kernel (tcgen05.mma kind::i8, int32 TMEM accumulators) + gram_quantize_kernel",
+                    "digit_products": engine.GRAM_TC_PRODUCTS, "ms": gram_ms, "algorithmic_tflops_per_gpu": achieved,
+                    "physical_int8_tops_per_gpu": achieved * engine.GRAM_TC_PRODUCTS * (p / 128 + 1) / (p / 128) },
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus,
+                        "frac_of_burst_peak": achieved / burst, "peak_source": src,
+                        "algorithmic_flop_per_launch_series": flop, "traffic": None,
+                        "note": "algorithmic flops n*p*(p+1) against the measured dense bf16 peak; the kernel issues "
+                                f"{engine.GRAM_TC_PRODUCTS} int8 digit products per output element (not credited)"},
+           "allreduce_payload_bytes": (p * p + 2 * p + 3) * 8 if world > 1 else 0,
+           "gpu_launches": int(launches),
+           "check": {"lambda_1": float(pca.eigs_all[0]), "lambda_20": float(pca.eigs_all[19])}}
+    # CPU: the reference's SIMCA.fit (two sklearn PCA fits + distances + limits) on a bounded sample of the same rows
+    try:
+        ref = reference_modules()
+        crow = 20000
+        Xc = synth.make_spectra(crow, p, seed=2000).astype(np.float32)
+        pool, cores = _all_cores()
+        with pool:
+            t0 = time.perf_counter()
+            if ref is not None:
+                import contextlib, io
+                np.random.seed(0)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ref[0].SIMCA(n_components=k, model_class=0, verbose=False).fit(Xc, np.zeros(crow, dtype=np.int64))
+                kind, what = "reference", "baseline/_ref utils/SIMCA.py SIMCA.fit"
+            else:
+                from oracle import simca_oracle as so
+                so.fit_one_class(Xc.astype(np.float64), k, faithful_solver=True)
+                kind, what = "port", "oracle.simca_oracle.fit_one_class"
+            cdt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": crow / cdt, "unit": "rows/s", "cores": cores, "kind": kind,
+                               "sample": f"one {what} on {crow} x {p} fp32 rows ({cdt:.1f} s)"}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
 
 
 def cv_leg(device, group=None, rank=0, world=1):
@@ -235,23 +384,32 @@ def cv_leg(device, group=None, rank=0, world=1):
            "n_gpus": world, "sharding": "folds dealt round-robin over ranks" if world > 1 else "one GPU",
            "best_LV": int(res["best_LV"]), "gpu_launches": native.launch_count() - l0,
            "timing": "host wall clock around the public call (includes H2D of X and host limit arithmetic)"}
-    # CPU: the oracle's per-(fold, A) fit + predict, bounded to 3 cells, extrapolated per fit
+    # CPU: the reference's own per-(fold, A) cell (SIMCA.fit on the fold's training rows + predict on its test rows,
+    # what CVSIMCA.py:183-190 does 200 times), bounded to 3 cells, reported per fit
     try:
-        from oracle import simca_oracle as so
         tr, te = next(iter(cv.split()))
-        Xtr = X[tr][y[tr] == 0]
+        ref = reference_modules()
         pool, cores = _all_cores()
         with pool:
             t0 = time.perf_counter()
             cells = 0
             for A in (5, 10, 15):
-                m = so.fit_one_class(Xtr, A, faithful_solver=True)
-                so.predict(m, X[te])
+                if ref is not None:
+                    import contextlib, io
+                    np.random.seed(0)
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        m = ref[0].SIMCA(n_components=A, model_class=0, verbose=False).fit(X[tr], y[tr])
+                        m.predict(X[te])
+                else:
+                    from oracle import simca_oracle as so
+                    m = so.fit_one_class(X[tr][y[tr] == 0], A, faithful_solver=True)
+                    so.predict(m, X[te])
                 cells += 1
             cdt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": cells / cdt, "unit": "fits/s", "cores": cores, "kind": "port",
-                               "sample": "3 (fold, A) cells of the same grid: oracle fit_one_class + predict"}
-    except Exception as e:  # the oracle is a checker; its absence must not kill the GPU line
+        out["cpu_baseline"] = {"value": cells / cdt, "unit": "fits/s", "cores": cores,
+                               "kind": "reference" if ref is not None else "port",
+                               "sample": "3 (fold, A) cells of the same grid: SIMCA.fit on the fold + predict on its test rows"}
+    except Exception as e:  # the CPU arm is a reported baseline; its absence must not kill the GPU line
         out["cpu_baseline"] = {"error": repr(e)}
     return out
 
@@ -273,6 +431,7 @@ def main():
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     p, A, rows = args.p, args.A, args.rows
+    peak, peak_src = measured_peak()
     pca, lim = fit_bench_model_gpu(p, A, device)
     mean32, P32 = pca.arrays32()
     Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=device)).float()
@@ -324,7 +483,6 @@ def main():
     accepted = int(out[2].sum().item())
 
     value = world * rows * args.steps / (total_ms_max * 1e-3)
-    peak, peak_src = measured_peak()
     achieved = BYTES_PER_SPECTRUM(p) * rows / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -334,11 +492,32 @@ def main():
         except Exception:
             traffic = None
 
+    # ---- strong scaling: the same `rows` in TOTAL, split over the ranks (BASELINE configs[2] "rows sharded over 1/2/4/8") ---
+    strong = None
+    if not args.no_strong:
+        lo, hi = odist.shard_rows(rows, rank, world)
+        Xs = X[: hi - lo]                              # this rank's shard size; the rows themselves are rank-private already
+        sstep = lambda: engine.score(Xs, mean32, P32, Sinv, rule="alt", ct=ct, cq=cq, dlim=lim.D_limit, force_simt=args.force_simt)
+        for _ in range(3):
+            sstep()
+        torch.cuda.synchronize(); barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            sstep()
+        s1.record()
+        torch.cuda.synchronize(); barrier()
+        sms_ = odist.max_over_ranks(s0.elapsed_time(s1), device)
+        strong = {"metric": "spectra scored/s (fused T2+Q)", "scaling": "strong", "rows_total": rows, "rows_per_gpu": hi - lo,
+                  "value": rows * args.steps / (sms_ * 1e-3), "unit": "spectra/s", "ms_per_step": sms_ / args.steps,
+                  "roofline_frac": BYTES_PER_SPECTRUM(p) * (hi - lo) / (sms_ / args.steps * 1e-3) / 1e9 / peak}
+
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) -----
     e2e = None
     if not args.no_e2e:
         import ctypes as C
         er = min(args.e2e_rows, rows)
+        numa = bind_to_gpu_numa_node(local_rank)       # before the pinned allocations: first touch on the GPU's own node
         hX = torch.empty((er, p), dtype=torch.float32).pin_memory()
         hX.copy_(X[:er])
         hT2 = torch.empty(er, dtype=torch.float32).pin_memory()
@@ -358,17 +537,35 @@ def main():
         torch.cuda.synchronize()
         edt = time.perf_counter() - t0
         edt = odist.max_over_ranks(edt, device)
+        # what the link itself gives: one bare pinned H2D copy of the same buffer, all ranks at once
+        dX = X[:er]
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            dX.copy_(hX, non_blocking=True)
+        torch.cuda.synchronize()
+        link = 2 * er * p * 4 / odist.max_over_ranks(time.perf_counter() - t0, device) / 1e9
         e2e = {"value": world * er * esteps / edt, "unit": "spectra/s",
                "h2d_bytes_per_step": int(er * p * 4), "d2h_bytes_per_step": int(er * 9),
                "rows_per_step": er, "steps": esteps,
+               "limit": {"what": "PCIe host->device link of each rank (the data plane of this call); the kernel needs 4 105 B per "
+                                 "spectrum from HBM at ~4.5 TB/s, the link delivers 4 096 B per spectrum at the rate below",
+                         "bare_pinned_h2d_gbs_per_rank": link, "achieved_gbs_per_rank": er * p * 4 * esteps / edt / 1e9,
+                         "host_binding": numa},
                "api": "ocm_simca_score_host_f32 (pinned host X -> T2,Q,accept on host; chunked double-buffered H2D)",
                "check": {"accepted_first_chunk": int(hA[: 1 << 10].sum().item())}}
         del hX
 
+    del X
+    torch.cuda.empty_cache()
+    fit_out = None
+    if not args.no_fit:
+        try:
+            fit_out = fit_leg(args, device, dist.group.WORLD if world > 1 else None, rank, world)
+        except Exception as e:
+            fit_out = {"error": repr(e)}
     cv_out = None
     if not args.no_cv:
-        del X
-        torch.cuda.empty_cache()
         try:
             cv_out = cv_leg(device, dist.group.WORLD if world > 1 else None, rank, world)
         except Exception as e:
@@ -385,7 +582,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": "one ncu --set full capture of this kernel (profiles/, dram__bytes_read + write per launch); not re-measured in this run",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SPECTRUM(p) * rows,
                      "kernel": kernel_name,
                      "kernel_ms": kernel_ms},
@@ -399,6 +597,10 @@ def main():
             line["cpu_baseline"] = cpu_baseline_leg(args)
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+    if strong is not None:
+        line["strong"] = strong
+    if fit_out is not None:
+        line["fit"] = fit_out
     if cv_out is not None:
         line["cv"] = cv_out
     print(json.dumps(line), flush=True)

@@ -32,6 +32,9 @@ extern "C" {
 #define OCM_EINVAL (-1)   /* bad argument (NULL pointer, non-positive size, unknown enum) */
 #define OCM_ELIMIT (-2)   /* size outside what the kernels support (e.g. n_components > 64) */
 #define OCM_EALIGN (-3)   /* pointer / leading dimension alignment not supported by this path */
+#define OCM_ETIMEOUT (-4) /* a tensor-core kernel of an EARLIER launch abandoned a bounded mbarrier wait; what it owned
+                             was written as NaN.  Reported once, by the next tensor-core call or by
+                             ocm_simca_score_tc_status(); the call that returns it has launched nothing. */
 
 /* preprocessing modes */
 #define OCM_PRE_SNV       1   /* (x - mean_row) / (std_row(ddof=0) + eps)      simca_nuts.py:48-50 */
@@ -178,9 +181,14 @@ int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
                            const float* mu, const float* P, const float* Sinv,
                            const ocm_score_params* h_params,
                            float* T2, float* Q, uint8_t* accept, void* stream);
-/* debugging aid: synchronises the device and returns 0 if no bounded mbarrier wait of the tcgen05
- * kernel ever timed out in this process, 1 if one did, -1 on a CUDA error */
+/* Synchronises the device, then returns and CLEARS the protocol status of the tcgen05 kernels (scoring and Gram):
+ * 0 = every launch so far completed its hand-offs, > 0 = a bounded mbarrier wait was abandoned (the kernel finished,
+ * the affected rows are NaN / rejected), -1 = CUDA error.  The scoring / Gram entry points check the same word
+ * (without synchronising) before they launch and return OCM_ETIMEOUT once. */
 int ocm_simca_score_tc_status(void);
+/* test hook: the next tcgen05 scoring launch drops one TMA stage in its first CTA, so that the bounded wait gives up
+ * after `max_polls` polls (>= 16).  Exists so that the failure path is exercised by the test-suite. */
+int ocm_simca_score_tc_inject_stall(int32_t max_polls);
 
 /* ---- a12: all nested models A = 1..Amax in one pass (CV grid, CVSIMCA.py:157-200) ------
  * inv_eig[Amax] = 1/lambda_a (diagonal Sinv of a PCA model).  Outputs are [n][Amax]:

@@ -15,7 +15,12 @@
 //                 the planes keep the row-major layout of X), 3-stage mbarrier ring of 64-row stages;
 //                 a chain is at most 32 704 rows (4 products x 2^14 x rows < 2^31), then
 //   3. flush      the int32 accumulators are combined in int64, converted to fp64, scaled by 2^-(sc_i + sc_j) and
-//                 added into the fp64 Gram with red.global.add.f64.
+//                 added into the CTA's own fp64 tile of a partial buffer (every (tile, K split) has exactly one owner, so
+//                 a plain vector read-modify-write: the first version used red.global.add.f64 and spent half its time
+//                 in 16 K atomics per CTA); one small kernel folds the partials into G at the end of the call.
+//   The diagonal of G does not come from the MMAs but from sum_r q^2 accumulated in fp64 by the quantiser, so it is
+//   exact to fp64 rounding whatever `products` is.  The quantiser of chunk c+1 runs on a side stream under the MMAs of
+//   chunk c (double-buffered planes).
 // The result is the exact Gram of the quantised data for `products` = 16; 13 drops the three products of weight
 // < 256^2 (relative error <= 2^-37 of max_i max_j per row), 10 those below 256^3 (<= 2^-28).  Column sums of v are
 // accumulated as int64 in the same pass, so cov = (G - N d d^T) / (N - 1) is the covariance OF THE QUANTISED ROWS to
@@ -24,6 +29,7 @@
 #include "ocm_common.cuh"
 #include "tc_ptx.cuh"
 
+#include <mutex>
 #include <stdlib.h>
 
 namespace ocm {
@@ -32,34 +38,67 @@ namespace gtc {
 using namespace ptx;
 
 constexpr int S = 4;                        // int8 digit planes
-constexpr int TILE = 128;                   // output tile edge = MMA M = MMA N
-constexpr int KB = 64;                      // rows per pipeline stage (two K = 32 MMAs per product)
-constexpr int NSTAGE = 3;
-constexpr int BOX_BYTES = TILE * KB;        // 8192: one plane's box, rows of 128 B, SWIZZLE_128B
-constexpr int STAGE_BYTES = 2 * S * BOX_BYTES;
+constexpr int TILE = 128;                   // row block of the output tile = MMA M; column blocks are TILE wide too
+constexpr int KB = 32;                      // rows per pipeline stage = K of one int8 MMA
+constexpr int BOX_BYTES = TILE * KB;        // 4096: one plane's box, 32 rows of 128 B, SWIZZLE_128B
 constexpr int NTHREADS = 192;               // warp 0: TMA, warp 1: MMA issue + TMEM owner, warps 2..5: flush
-constexpr int MAX_CHAIN_ROWS = 32704;       // 4 products x 128 x 128 x rows < 2^31, multiple of KB
+constexpr int MAX_CHAIN_ROWS = 32704;       // 4 products x 128 x 128 x rows < 2^31
 constexpr int V_LIMIT = 0x5FFFFFFF;         // clamp of the fixed-point value (top digit stays <= 96)
-constexpr size_t SM_OFF_BAR = (size_t)NSTAGE * STAGE_BYTES;
-constexpr size_t SM_TOTAL = SM_OFF_BAR + 128 + 1024;      // + barriers + slack for the 1024-byte alignment
+constexpr int QROWS = 64;                   // the quantiser pads a chunk to a multiple of this many rows
+// NB = column blocks per CTA tile.  NB = 1: 128 x 128 tiles, four accumulators (one pass over the data for the ten
+// leading products).  NB = 2: 128 x 256 tiles, MMA N = 256, two accumulators, two weights per pass -- at N = 128 the
+// operand reads of the MMAs (8 KB per 64 cycles = 128 B/clk) plus the TMA writes of the next stage exceed the
+// 128 B/clk of the shared-memory pipe (measured: 62 % of the MMA rate); at N = 256 an MMA reads 12 KB per 128 cycles.
+template <int NB> struct Cfg {
+    static constexpr int STAGE_BYTES = (S + S * NB) * BOX_BYTES;          // A planes + B planes x column blocks
+    static constexpr int NSTAGE = NB == 1 ? 6 : 4;
+    static constexpr size_t SM_OFF_BAR = (size_t)NSTAGE * STAGE_BYTES;
+    static constexpr size_t SM_TOTAL = SM_OFF_BAR + 128 + 1024;           // + barriers + slack for the 1024-byte alignment
+    static constexpr int MAX_ACC = 4 / NB;
+};
 
 struct Products {
     int n;                  // number of (k, l) digit products in this launch
-    int nacc;               // accumulators used (each TILE columns of TMEM)
-    int nload;              // digit planes 0 .. nload-1 are loaded
+    int nacc;               // accumulators used (each TILE * NB columns of TMEM)
+    int kmin, nload;        // digit planes kmin .. nload-1 are loaded
     int dmin;               // weight of accumulator 0 is 256^dmin, accumulator a is 256^(dmin + a)
     uint8_t k[16], l[16], acc[16];
 };
 
 struct Args {
     int p;                  // columns of G
-    int nt;                 // tiles per edge
+    int nt;                 // 128-column blocks per edge
+    int ntiles;             // CTA tiles (upper triangle)
     int nstages;            // stages in this chunk (rows_pad / KB)
     int stages_per_split;
     const double* inv_scale;    // [p_pad] 2^-sc
-    double* G;              // [p][p] upper triangle accumulated into
+    double* part;           // [splits][ntiles][8 NB][128][16] fp64 partial tiles, each owned by ONE CTA of a launch
+    unsigned int* status;   // protocol status word (mapped host memory), see mbar_wait_bounded
     Products pr;
 };
+
+// tile index -> (row block ti, first column block tj); NB = 2 tiles cover column blocks tj, tj + 1 with tj even
+template <int NB>
+__host__ __device__ inline void tile_coords(int tile, int nt, int& ti, int& tj) {
+    if (NB == 1) {
+        int t = tile; ti = 0;
+        while (t >= nt - ti) { t -= nt - ti; ++ti; }
+        tj = ti + t;
+    } else {
+        const int nt2 = (nt + 1) / 2;
+        int t = tile; ti = 0;
+        while (t >= nt2 - ti / 2) { t -= nt2 - ti / 2; ++ti; }
+        tj = 2 * (ti / 2 + t);
+    }
+}
+template <int NB>
+inline int tile_count(int nt) {
+    if (NB == 1) return nt * (nt + 1) / 2;
+    const int nt2 = (nt + 1) / 2;
+    int c = 0;
+    for (int ti = 0; ti < nt; ++ti) c += nt2 - ti / 2;
+    return c;
+}
 
 // ------------------------------------------------------------------------------------------ quantise
 // One warp = one row x 128 columns per step (lane -> 4 consecutive columns), 8 warps walk the rows of the block's slab.
@@ -68,7 +107,8 @@ __global__ void __launch_bounds__(256)
 gram_quantize_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __restrict__ row_idx, int64_t r0, int rows,
                      int rows_pad, int p, int p_pad, const double* __restrict__ shift, const double* __restrict__ scale,
                      uint8_t* __restrict__ planes, int64_t plane_stride, long long* __restrict__ colsum_q,
-                     unsigned long long* __restrict__ flags, int rows_per_block, int vec_ok) {
+                     double* __restrict__ colsumsq_q, unsigned long long* __restrict__ flags, int rows_per_block,
+                     int vec_ok) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * TILE + 4 * lane;
     const int rb = blockIdx.y * rows_per_block;
@@ -81,6 +121,7 @@ gram_quantize_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __rest
         sc[e] = ok ? scale[c0 + e] : 0.0;
     }
     long long cs[4] = {0, 0, 0, 0};
+    double css[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned int clamped = 0, nonfinite = 0;
     for (int r = rb + warp; r < re; r += 8) {
         float x[4] = {0.f, 0.f, 0.f, 0.f};
@@ -113,6 +154,8 @@ gram_quantize_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __rest
             if (v > V_LIMIT) { v = V_LIMIT; ++clamped; }
             if (v < -V_LIMIT) { v = -V_LIMIT; ++clamped; }
             cs[e] += v;
+            const double vd = (double)v;
+            css[e] = fma(vd, vd, css[e]);
             w[e] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;   // bytes = balanced digits d0..d3
         }
         // byte transpose: plane k gets byte k of the four columns
@@ -127,15 +170,18 @@ gram_quantize_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __rest
         *reinterpret_cast<uint32_t*>(out + 3 * plane_stride) = d3;
     }
     __shared__ long long s_cs[8][TILE];
+    __shared__ double s_css[8][TILE];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) s_cs[warp][4 * lane + e] = cs[e];
+    for (int e = 0; e < 4; ++e) { s_cs[warp][4 * lane + e] = cs[e]; s_css[warp][4 * lane + e] = css[e]; }
     __syncthreads();
     if (threadIdx.x < TILE) {
         long long t = 0;
+        double t2 = 0.0;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) t += s_cs[w8][threadIdx.x];
+        for (int w8 = 0; w8 < 8; ++w8) { t += s_cs[w8][threadIdx.x]; t2 += s_css[w8][threadIdx.x]; }
         const int c = blockIdx.x * TILE + threadIdx.x;
         if (c < p && t != 0) atomicAdd(reinterpret_cast<unsigned long long*>(colsum_q + c), (unsigned long long)t);
+        if (c < p && t2 != 0.0) atomicAdd(colsumsq_q + c, t2);
     }
     clamped = __reduce_add_sync(0xffffffffu, clamped);
     nonfinite = __reduce_add_sync(0xffffffffu, nonfinite);
@@ -148,9 +194,11 @@ gram_quantize_kernel(const T* __restrict__ X, int64_t ldx, const int64_t* __rest
 // scale[j] = 2^sc, inv_scale[j] = 2^-sc with sc = 30 - e, max|x - shift| = f 2^e (f in [0.5, 1)): |v| <= 2^30
 __global__ void gram_scale_kernel(const float* __restrict__ colmin, const float* __restrict__ colmax,
                                   const double* __restrict__ shift, int p, int p_pad, double* __restrict__ scale,
-                                  double* __restrict__ inv_scale, long long* __restrict__ colsum_q) {
+                                  double* __restrict__ inv_scale, long long* __restrict__ colsum_q,
+                                  double* __restrict__ colsumsq_q) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= p_pad) return;
+    colsumsq_q[j] = 0.0;
     int sc = 0;
     if (j < p) {
         const double m = fmax((double)colmax[j] - shift[j], shift[j] - (double)colmin[j]) * (1.0 + 1e-6);
@@ -167,6 +215,31 @@ __global__ void gram_scale_kernel(const float* __restrict__ colmin, const float*
     colsum_q[j] = 0;
 }
 
+// G[i][j] += sum over K splits of the partial tiles (upper triangle); the diagonal comes from the quantiser's sum q^2
+template <int NB>
+__global__ void __launch_bounds__(256)
+gram_fold_kernel(const double* __restrict__ part, int splits, int nt, int ntiles, int p, const double* __restrict__ colsumsq_q,
+                 const double* __restrict__ inv_scale, double* __restrict__ G) {
+    const int tile = blockIdx.x;
+    int ti, tj;
+    tile_coords<NB>(tile, nt, ti, tj);
+    constexpr int TW = TILE * NB, TSZ = TILE * TW;
+    for (int idx = threadIdx.x; idx < TSZ; idx += blockDim.x) {
+        const int r = idx / TW, c = idx % TW;
+        const int i = ti * TILE + r, j = tj * TILE + c;
+        if (i >= p || j >= p || j < i) continue;
+        double acc;
+        if (i == j) {
+            acc = colsumsq_q[i] * inv_scale[i] * inv_scale[i];
+        } else {
+            acc = 0.0;
+            const int64_t off = ((int64_t)(c >> 4) * TILE + r) * 16 + (c & 15);
+            for (int sp = 0; sp < splits; ++sp) acc += part[((int64_t)sp * ntiles + tile) * (int64_t)TSZ + off];
+        }
+        G[(int64_t)i * p + j] += acc;
+    }
+}
+
 __global__ void gram_colsum_kernel(const long long* __restrict__ colsum_q, const double* __restrict__ inv_scale, int p,
                                    double* __restrict__ colsum) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,29 +247,32 @@ __global__ void gram_colsum_kernel(const long long* __restrict__ colsum_q, const
 }
 
 // ------------------------------------------------------------------------------------------ multiply
+template <int NB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Args a) {
+    using C = Cfg<NB>;
+    constexpr int NSTAGE = C::NSTAGE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms are 1024-byte aligned
-    const uint32_t bar0 = sb + (uint32_t)SM_OFF_BAR;
+    const uint32_t bar0 = sb + (uint32_t)C::SM_OFF_BAR;
     auto BAR_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(NSTAGE + s); };
     const uint32_t bar_acc = bar0 + 8u * (uint32_t)(2 * NSTAGE);
     const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * NSTAGE + 1);
+    const WaitCtx wctx{tmem_slot + 4u, a.status, 1u << 22};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // work unit: (upper-triangle tile, K split)
-    const int ntiles = a.nt * (a.nt + 1) / 2;
-    const int tile = blockIdx.x % ntiles, split = blockIdx.x / ntiles;
-    int t = tile, ti = 0;
-    while (t >= a.nt - ti) { t -= a.nt - ti; ++ti; }
-    const int tj = ti + t;
-    const bool diag = ti == tj;
+    const int tile = blockIdx.x % a.ntiles, split = blockIdx.x / a.ntiles;
+    int ti, tj;
+    tile_coords<NB>(tile, a.nt, ti, tj);
+    const bool diag = NB == 1 && ti == tj;                      // B is A: load the planes once
     const int st0 = split * a.stages_per_split;
     const int nst = min(a.nstages, st0 + a.stages_per_split) - st0;
     if (nst <= 0) return;                                        // uniform over the CTA
 
     if (tid == 0) {
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(wctx.abort_addr), "r"(0u) : "memory");
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
         mbar_init(bar_acc, 1);
         fence_mbar_init();
@@ -210,84 +286,92 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
-        // ===== TMA producer: digit planes of the tile's row block (A) and column block (B) ===================
+        // ===== TMA producer: digit planes of the tile's row block (A) and column block(s) (B) ================
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();          // every box is read by up to nt tiles: keep it in L2
-            const uint32_t bytes = (uint32_t)((diag ? 1 : 2) * a.pr.nload * BOX_BYTES);
+            const uint32_t bytes = (uint32_t)((diag ? 1 : 1 + NB) * (a.pr.nload - a.pr.kmin) * BOX_BYTES);
             int slot = 0;
             uint32_t ph = 0;
             for (int s = 0; s < nst; ++s) {
-                mbar_wait_or_trap(BAR_EMPTY(slot), ph ^ 1u);
+                if (!mbar_wait_bounded(BAR_EMPTY(slot), ph ^ 1u, wctx, 11u)) break;
                 mbar_expect_tx(BAR_FULL(slot), bytes);
-                const uint32_t dst = sb + (uint32_t)slot * (uint32_t)STAGE_BYTES;
+                const uint32_t dst = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
                 const int row = (st0 + s) * KB;
-                for (int k = 0; k < a.pr.nload; ++k)
+                for (int k = a.pr.kmin; k < a.pr.nload; ++k)
                     tma_load_3d(dst + (uint32_t)(k * BOX_BYTES), &tmap, ti * TILE, row, k, BAR_FULL(slot), pol);
                 if (!diag)
-                    for (int k = 0; k < a.pr.nload; ++k)
-                        tma_load_3d(dst + (uint32_t)((S + k) * BOX_BYTES), &tmap, tj * TILE, row, k, BAR_FULL(slot), pol);
+                    for (int k = a.pr.kmin; k < a.pr.nload; ++k)
+#pragma unroll
+                        for (int cb = 0; cb < NB; ++cb)        // columns beyond p_pad are zero-filled by the TMA
+                            tma_load_3d(dst + (uint32_t)((S + k * NB + cb) * BOX_BYTES), &tmap, (tj + cb) * TILE, row, k,
+                                        BAR_FULL(slot), pol);
                 if (++slot == NSTAGE) { slot = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issue: warp-uniform loop, one elected lane issues ============================================
-        constexpr uint32_t IDESC = make_idesc_i8(TILE, TILE, true, true);
+        constexpr uint32_t IDESC = make_idesc_i8(TILE, TILE * NB, true, true);
         const uint32_t b_off = diag ? 0u : (uint32_t)(S * BOX_BYTES);
         uint32_t used = 0;
         int slot = 0;
         uint32_t ph = 0;
         for (int s = 0; s < nst; ++s) {
-            mbar_wait_or_trap(BAR_FULL(slot), ph);
+            if (!mbar_wait_bounded(BAR_FULL(slot), ph, wctx, 12u)) break;
             tc_fence_after();
-            const uint32_t base = sb + (uint32_t)slot * (uint32_t)STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < KB / 32; ++ks) {
-                // MN-major SW128 operand: 128 columns = one 128-byte atom row, 8-row groups 1024 B apart (SBO); one
-                // K = 32 MMA covers four groups; the next k-step starts 4096 B further
-                for (int m = 0; m < a.pr.n; ++m) {
-                    const uint32_t acc = a.pr.acc[m];
-                    const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * BOX_BYTES + (uint32_t)ks * 4096u, BOX_BYTES, 1024);
-                    const uint64_t db = make_desc_sw128(base + b_off + (uint32_t)a.pr.l[m] * BOX_BYTES + (uint32_t)ks * 4096u, BOX_BYTES, 1024);
-                    tc_mma_ss_i8(tmem + acc * (uint32_t)TILE, da, db, IDESC, (used >> acc) & 1u);
-                    used |= 1u << acc;
-                }
+            const uint32_t base = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
+            // MN-major SW128 operands: 128 columns = one 128-byte atom row, 8-row groups 1024 B apart (SBO), one K = 32
+            // MMA covers the four groups of a box; the B operand of an N = 256 MMA is two atoms BOX_BYTES apart (LBO)
+            for (int m = 0; m < a.pr.n; ++m) {
+                const uint32_t acc = a.pr.acc[m];
+                const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * BOX_BYTES, BOX_BYTES, 1024);
+                const uint64_t db = make_desc_sw128(base + b_off + (uint32_t)a.pr.l[m] * (uint32_t)(NB * BOX_BYTES), BOX_BYTES, 1024);
+                tc_mma_ss_i8(tmem + acc * (uint32_t)(TILE * NB), da, db, IDESC, (used >> acc) & 1u);
+                used |= 1u << acc;
             }
             tc_commit_elect(BAR_EMPTY(slot));                   // the slot is free once these MMAs have read it
             if (++slot == NSTAGE) { slot = 0; ph ^= 1u; }
         }
         tc_commit_elect(bar_acc);
     } else {
-        // ===== flush: int32 accumulators -> int64 -> fp64 -> red.add into G ====================================
+        // ===== flush: int32 accumulators -> int64 -> fp64 -> += into this CTA's own partial tile ====================
         const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
-        mbar_wait_or_trap(bar_acc, 0);
+        const bool ok = mbar_wait_bounded(bar_acc, 0, wctx, 13u);      // false: the pipeline gave up -> the tile becomes NaN
         tc_fence_after();
-        const int i = ti * TILE + 32 * q + lane;
-        const double w_i = i < a.p ? ldexp(a.inv_scale[i], 8 * a.pr.dmin) : 0.0;
+        const int r = 32 * q + lane;                             // row of the tile
+        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * a.pr.dmin);
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-        for (int c16 = 0; c16 < TILE / 16; ++c16) {
+        // partial tile layout [c16][row][16]: a warp's 32 rows x 128 B are one contiguous 4 KB run per column group
+        double* tile_base = a.part + ((int64_t)split * a.ntiles + tile) * (int64_t)(TILE * TILE * NB);
+        const int ncol_ok = a.nt * TILE - tj * TILE;             // columns of this tile inside the padded matrix
+        for (int c16 = 0; c16 < NB * TILE / 16; ++c16) {
+            if (16 * c16 >= ncol_ok) break;                      // second column block of an odd edge: nothing there
             long long tsum[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) tsum[e] = 0;
             for (int ac = 0; ac < a.pr.nacc; ++ac) {
                 uint32_t v[16];
-                tc_ld16(lane_addr + (uint32_t)(ac * TILE + 16 * c16), v);
+                tc_ld16(lane_addr + (uint32_t)(ac * TILE * NB + 16 * c16), v);
                 tc_wait_ld();
                 tc_pin16(v);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) tsum[e] += (long long)(int)v[e] << (8 * ac);
             }
-            const int j0 = tj * TILE + 16 * c16;
-            if (i < a.p) {
+            const double* isc = a.inv_scale + tj * TILE + 16 * c16;
+            double2* dst = reinterpret_cast<double2*>(tile_base + ((int64_t)c16 * TILE + r) * 16);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = j0 + e;
-                    if (j < a.p && j >= i && tsum[e] != 0)
-                        atomicAdd(a.G + (int64_t)i * a.p + j, (double)tsum[e] * (w_i * a.inv_scale[j]));
-                }
+            for (int e = 0; e < 8; ++e) {
+                double2 cur = dst[e];
+                cur.x += (double)tsum[2 * e] * (w_i * isc[2 * e]);
+                cur.y += (double)tsum[2 * e + 1] * (w_i * isc[2 * e + 1]);
+                if (!ok) cur.x = cur.y = __longlong_as_double(0x7ff8000000000000ll);
+                dst[e] = cur;
             }
         }
         tc_fence_before();
+    }
+    if (lds32_volatile(wctx.abort_addr)) {     // in-flight TMA boxes / MMAs of the abandoned pipeline: let them land
+        for (int i = 0; i < 100; ++i) __nanosleep(2000);
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512u);
@@ -298,7 +382,7 @@ static int make_planes_map(CUtensorMap* map, const uint8_t* planes, int p_pad, i
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return (int)cudaErrorNotSupported; }
     const cuuint64_t dims[3] = {(cuuint64_t)p_pad, (cuuint64_t)rows_cap, (cuuint64_t)S};
     const cuuint64_t strides[2] = {(cuuint64_t)p_pad, (cuuint64_t)p_pad * (cuuint64_t)rows_cap};
-    const cuuint32_t box[3] = {(cuuint32_t)TILE, (cuuint32_t)KB, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)TILE, (cuuint32_t)KB, 1};      // 128 columns x 32 rows of one plane
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(planes), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -312,7 +396,7 @@ static Products product_table(int dlo, int dhi) {
     Products pr{};
     pr.dmin = dlo;
     pr.nacc = dhi - dlo + 1;
-    int kmax = 0;
+    int kmax = 0, kmin = S;
     for (int d = dlo; d <= dhi; ++d)
         for (int k = 0; k < S; ++k) {
             const int l = d - k;
@@ -321,30 +405,94 @@ static Products product_table(int dlo, int dhi) {
             ++pr.n;
             if (k > kmax) kmax = k;
             if (l > kmax) kmax = l;
+            if (k < kmin) kmin = k;
+            if (l < kmin) kmin = l;
         }
     pr.nload = kmax + 1;
+    pr.kmin = kmin;
     return pr;
 }
 
+// K splits of a chunk: every (tile, split) is one CTA with its own partial tile.  Cost model in cycles: 64 NB cycles
+// per MMA, ~15 k cycles of set-up + flush per CTA; whole waves of `sms` CTAs.
+static int choose_splits(int ntiles, int nstages, int sms, int nprod, int nb) {
+    int max_splits = ntiles >= sms ? 1 : sms / ntiles;
+    if (max_splits > nstages) max_splits = nstages;
+    if (max_splits < 1) max_splits = 1;
+    int best_sp = 1;
+    double best = 1e300;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const int64_t waves = ((int64_t)ntiles * sp + sms - 1) / sms;
+        const double cost = (double)waves * ((double)((nstages + sp - 1) / sp) * 64.0 * nb * nprod + 15000.0);
+        if (cost < best * 0.999) { best = cost; best_sp = sp; }
+    }
+    return best_sp;
+}
+
+static int column_blocks() {       // OCM_GRAM_NB=1 selects the 128 x 128 tile kernel (A/B runs); default 128 x 256
+    static const int nb = [] { const char* e = getenv("OCM_GRAM_NB"); return (e && e[0] == '1') ? 1 : 2; }();
+    return nb;
+}
+
 struct Layout {
-    int p_pad, rows_cap;
-    size_t off_scale, off_inv, off_colsum, off_flags, off_planes, total;
+    int nb, p_pad, rows_cap, nt, ntiles, max_splits;
+    size_t off_scale, off_inv, off_colsum, off_colsumsq, off_flags, off_part, off_planes, plane_buf_bytes, total;
 };
 static Layout workspace_layout(int64_t n, int p) {
     Layout L;
+    L.nb = column_blocks();
     L.p_pad = (p + TILE - 1) / TILE * TILE;
-    int64_t rc = (n + KB - 1) / KB * KB;
+    L.nt = L.p_pad / TILE;
+    L.ntiles = L.nb == 1 ? tile_count<1>(L.nt) : tile_count<2>(L.nt);
+    int64_t rc = (n + QROWS - 1) / QROWS * QROWS;
     if (rc > MAX_CHAIN_ROWS) rc = MAX_CHAIN_ROWS;
+    if (rc < QROWS) rc = QROWS;
     L.rows_cap = (int)rc;
+    const int sms = sm_count();
+    L.max_splits = L.ntiles >= sms ? 1 : sms / L.ntiles;
     size_t o = 0;
     L.off_scale = o; o += sizeof(double) * L.p_pad;
-    L.off_inv = o; o += sizeof(double) * L.p_pad;
+    L.off_inv = o; o += sizeof(double) * (L.p_pad + TILE);      // + one block: the padded second column block of an odd edge
     L.off_colsum = o; o += sizeof(long long) * L.p_pad;
+    L.off_colsumsq = o; o += sizeof(double) * L.p_pad;
     L.off_flags = o; o += 64;
     o = (o + 1023) / 1024 * 1024;
-    L.off_planes = o; o += (size_t)S * L.rows_cap * L.p_pad;
+    L.off_part = o; o += sizeof(double) * (size_t)L.max_splits * L.ntiles * TILE * TILE * L.nb;
+    o = (o + 1023) / 1024 * 1024;
+    L.plane_buf_bytes = (size_t)S * L.rows_cap * L.p_pad;
+    const int nbuf = n > L.rows_cap ? 2 : 1;                 // double-buffered when there is more than one chunk
+    L.off_planes = o; o += (size_t)nbuf * L.plane_buf_bytes;
     L.total = o;
     return L;
+}
+
+// side stream + events for running the quantiser of chunk c+1 under the MMAs of chunk c (one set per device)
+struct Side {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, q_done[2] = {nullptr, nullptr}, g_done[2] = {nullptr, nullptr};
+    std::mutex mu;
+};
+static Side* side_of_device(int dev) {
+    static Side sides[64];
+    if (dev < 0 || dev >= 64) return nullptr;
+    Side* sd = &sides[dev];
+    if (!sd->stream) {
+        if (cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventCreateWithFlags(&sd->q_done[b], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&sd->g_done[b], cudaEventDisableTiming);
+        }
+    }
+    return sd;
+}
+
+template <int NB>
+static int launch_gram(const CUtensorMap& tmap, const Args& a, int ctas, cudaStream_t stream) {
+    auto kern = gram_tc_kernel<NB>;
+    OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NB>::SM_TOTAL));
+    kern<<<(unsigned)ctas, NTHREADS, Cfg<NB>::SM_TOTAL, stream>>>(tmap, a);
+    return check_launch("gram_tc_kernel");
 }
 
 template <typename T>
@@ -355,6 +503,10 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
     OCM_REQUIRE(X && shift && colmin && colmax && work && G && n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape or NULL buffer");
     OCM_REQUIRE(products == 10 || products == 13 || products == 16, OCM_EINVAL, "products must be 10, 13 or 16");
     OCM_REQUIRE(p <= 128 * 181, OCM_ELIMIT, "p too large for the tile index");
+    {
+        const int st = tc_status_report("ocm_gram_tc");       // an EARLIER tensor-core launch gave up: say so first
+        if (st) return st;
+    }
     const Layout L = workspace_layout(n, p);
     OCM_REQUIRE(work_bytes >= L.total, OCM_EINVAL, "workspace too small (see ocm_gram_tc_workspace_bytes)");
     OCM_REQUIRE((reinterpret_cast<uintptr_t>(work) & 1023) == 0, OCM_EALIGN, "workspace must be 1024-byte aligned");
@@ -363,63 +515,90 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
     double* scale = reinterpret_cast<double*>(wb + L.off_scale);
     double* inv_scale = reinterpret_cast<double*>(wb + L.off_inv);
     long long* colsum_q = reinterpret_cast<long long*>(wb + L.off_colsum);
+    double* colsumsq_q = reinterpret_cast<double*>(wb + L.off_colsumsq);
     unsigned long long* wflags = reinterpret_cast<unsigned long long*>(wb + L.off_flags);
-    uint8_t* planes = wb + L.off_planes;
+    double* part = reinterpret_cast<double*>(wb + L.off_part);
     const int64_t plane_stride = (int64_t)L.rows_cap * L.p_pad;
+    const int sms = sm_count();
+    const int64_t nchunks = (n + L.rows_cap - 1) / L.rows_cap;
+
+    // passes: which weights 256^d go into which launch (one accumulator per weight, 4 / NB accumulators per launch)
+    Products passes[4];
+    int npass = 0;
+    if (L.nb == 1) {
+        passes[npass++] = product_table(3, 6);
+        if (products == 13) passes[npass++] = product_table(2, 2);
+        if (products == 16) passes[npass++] = product_table(0, 2);
+    } else {
+        passes[npass++] = product_table(3, 4);
+        passes[npass++] = product_table(5, 6);
+        if (products >= 13) passes[npass++] = product_table(2, 2);
+        if (products == 16) passes[npass++] = product_table(0, 1);
+    }
+
+    // the K split is fixed for the call (the partial buffer is indexed by it); the last, shorter chunk just has fewer stages
+    const int nstages_full = (int)(((n < L.rows_cap ? n : L.rows_cap) + KB - 1) / KB);
+    int splits = choose_splits(L.ntiles, nstages_full, sms, passes[0].n, L.nb);
+    if (splits > L.max_splits) splits = L.max_splits;
 
     OCM_CUDA(cudaMemsetAsync(wflags, 0, 64, stream));
-    gram_scale_kernel<<<(L.p_pad + 255) / 256, 256, 0, stream>>>(colmin, colmax, shift, p, L.p_pad, scale, inv_scale, colsum_q);
+    OCM_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)splits * L.ntiles * TILE * TILE * L.nb, stream));
+    OCM_CUDA(cudaMemsetAsync(inv_scale + L.p_pad, 0, sizeof(double) * TILE, stream));
+    gram_scale_kernel<<<(L.p_pad + 255) / 256, 256, 0, stream>>>(colmin, colmax, shift, p, L.p_pad, scale, inv_scale, colsum_q, colsumsq_q);
     int rc = check_launch("gram_scale_kernel");
     if (rc) return rc;
 
-    CUtensorMap tmap;
-    rc = make_planes_map(&tmap, planes, L.p_pad, L.rows_cap);
-    if (rc) return rc;
-    auto kern = gram_tc_kernel;
-    OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-
-    const int nt = L.p_pad / TILE, ntiles = nt * (nt + 1) / 2, sms = sm_count();
+    CUtensorMap tmap[2];
+    for (int b = 0; b < (nchunks > 1 ? 2 : 1); ++b) {
+        rc = make_planes_map(&tmap[b], wb + L.off_planes + (size_t)b * L.plane_buf_bytes, L.p_pad, L.rows_cap);
+        if (rc) return rc;
+    }
     const int vec_ok = (sizeof(T) == 4 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) ? 1 : 0;
-    Products passes[2];
-    int npass = 1;
-    passes[0] = product_table(3, 6);
-    if (products == 13) { passes[1] = product_table(2, 2); npass = 2; }
-    if (products == 16) { passes[1] = product_table(0, 2); npass = 2; }
 
-    for (int64_t r0 = 0; r0 < n; r0 += L.rows_cap) {
+    // several chunks: quantise chunk c+1 on the side stream while the MMAs of chunk c run on the caller's stream
+    int dev = 0;
+    OCM_CUDA(cudaGetDevice(&dev));
+    Side* sd = nchunks > 1 ? side_of_device(dev) : nullptr;
+    std::unique_lock<std::mutex> lock;
+    cudaStream_t qstream = stream;
+    if (sd) {
+        lock = std::unique_lock<std::mutex>(sd->mu);
+        qstream = sd->stream;
+        OCM_CUDA(cudaEventRecord(sd->fork, stream));
+        OCM_CUDA(cudaStreamWaitEvent(qstream, sd->fork, 0));
+    }
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = sd ? (int)(c & 1) : 0;
+        const int64_t r0 = c * L.rows_cap;
         const int rows = (int)((n - r0 < L.rows_cap) ? n - r0 : L.rows_cap);
-        const int rows_pad = (rows + KB - 1) / KB * KB;
+        const int rows_pad = (rows + QROWS - 1) / QROWS * QROWS;
+        uint8_t* planes = wb + L.off_planes + (size_t)b * L.plane_buf_bytes;
         const int rpb = 256;
-        dim3 qgrid(nt, (rows_pad + rpb - 1) / rpb);
-        gram_quantize_kernel<T><<<qgrid, 256, 0, stream>>>(X, ldx, row_idx, r0, rows, rows_pad, p, L.p_pad, shift, scale,
-                                                           planes, plane_stride, colsum_q, wflags, rpb, vec_ok);
+        dim3 qgrid(L.nt, (rows_pad + rpb - 1) / rpb);
+        if (sd && c >= 2) OCM_CUDA(cudaStreamWaitEvent(qstream, sd->g_done[b], 0));     // the buffer's previous MMAs are done
+        gram_quantize_kernel<T><<<qgrid, 256, 0, qstream>>>(X, ldx, row_idx, r0, rows, rows_pad, p, L.p_pad, shift, scale,
+                                                            planes, plane_stride, colsum_q, colsumsq_q, wflags, rpb, vec_ok);
         rc = check_launch("gram_quantize_kernel");
         if (rc) return rc;
-        const int nstages = rows_pad / KB;
-        // K splits: fill the SMs with whole waves; every CTA flushes a 128 x 128 tile, so keep >= 16 stages each
-        int splits = 1;
-        {
-            int max_splits = nstages / 16;
-            if (max_splits < 1) max_splits = 1;
-            double best = 0.0;
-            for (int sp = 1; sp <= max_splits && sp <= 4 * sms; ++sp) {
-                const int64_t ctas = (int64_t)ntiles * sp, waves = (ctas + sms - 1) / sms;
-                const double eff = (double)ctas / (double)(waves * sms);
-                if (eff > best + 0.01) { best = eff; splits = sp; }
-            }
+        if (sd) {
+            OCM_CUDA(cudaEventRecord(sd->q_done[b], qstream));
+            OCM_CUDA(cudaStreamWaitEvent(stream, sd->q_done[b], 0));
         }
         Args a{};
-        a.p = p; a.nt = nt; a.nstages = nstages;
-        a.stages_per_split = (nstages + splits - 1) / splits;
-        splits = (nstages + a.stages_per_split - 1) / a.stages_per_split;
-        a.inv_scale = inv_scale; a.G = G;
+        a.p = p; a.nt = L.nt; a.ntiles = L.ntiles; a.nstages = (rows + KB - 1) / KB;
+        a.stages_per_split = (nstages_full + splits - 1) / splits;
+        a.inv_scale = inv_scale; a.part = part; a.status = tc_status_device_ptr();
         for (int ps = 0; ps < npass; ++ps) {
             a.pr = passes[ps];
-            kern<<<(unsigned)(ntiles * splits), NTHREADS, SM_TOTAL, stream>>>(tmap, a);
-            rc = check_launch("gram_tc_kernel");
+            rc = L.nb == 1 ? launch_gram<1>(tmap[b], a, L.ntiles * splits, stream) : launch_gram<2>(tmap[b], a, L.ntiles * splits, stream);
             if (rc) return rc;
         }
+        if (sd) OCM_CUDA(cudaEventRecord(sd->g_done[b], stream));
     }
+    if (L.nb == 1) gram_fold_kernel<1><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
+    else gram_fold_kernel<2><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
+    rc = check_launch("gram_fold_kernel");
+    if (rc) return rc;
     if (colsum) {
         gram_colsum_kernel<<<(p + 255) / 256, 256, 0, stream>>>(colsum_q, inv_scale, p, colsum);
         rc = check_launch("gram_colsum_kernel");

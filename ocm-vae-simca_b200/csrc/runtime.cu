@@ -32,6 +32,50 @@ int sm_count() {
     return cached;
 }
 
+// ---- protocol status of the tcgen05 kernels ---------------------------------------------------------------
+// One 32-bit word per device in MAPPED pinned host memory: a kernel whose bounded mbarrier wait gives up writes a
+// non-zero code there (and NaN-poisons its outputs); the host reads the word without touching the device, at the
+// entry of the next call and after the synchronising calls, reports OCM_ETIMEOUT once and clears it -- a later
+// launch never inherits the flag.
+namespace {
+struct StatusWord { unsigned int* host = nullptr; unsigned int* dev = nullptr; };
+StatusWord g_status[64];
+}
+
+unsigned int* tc_status_device_ptr() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    StatusWord& w = g_status[dev];
+    if (!w.host) {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        w.host = static_cast<unsigned int*>(h);
+        for (int i = 0; i < 16; ++i) w.host[i] = 0;
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaFreeHost(h); w.host = nullptr; return nullptr; }
+        w.dev = static_cast<unsigned int*>(d);
+    }
+    return w.dev;
+}
+
+int tc_status_take() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    StatusWord& w = g_status[dev];
+    if (!w.host) return 0;
+    const unsigned int v = *reinterpret_cast<volatile unsigned int*>(w.host);
+    if (v) *reinterpret_cast<volatile unsigned int*>(w.host) = 0;
+    return (int)v;
+}
+
+int tc_status_report(const char* where) {
+    const int v = tc_status_take();
+    if (!v) return 0;
+    set_error("%s: a tcgen05 kernel of an EARLIER launch gave up a bounded mbarrier wait (code %d); the rows / tiles it "
+              "owned were written as NaN", where, v);
+    return OCM_ETIMEOUT;
+}
+
 }  // namespace ocm
 
 extern "C" int ocm_abi_version(void) { return OCM_ABI_VERSION; }

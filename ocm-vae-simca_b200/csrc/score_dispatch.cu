@@ -126,5 +126,5 @@ extern "C" int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, 
     }
     for (int k = 0; k < 2; ++k) OCM_TRY(cudaStreamSynchronize(w.st[k]));
 #undef OCM_TRY
-    return 0;
+    return tc_status_report("ocm_simca_score_host_f32");      // everything has completed: the status word is exact here
 }

@@ -49,6 +49,7 @@
 // 35 %, DRAM traffic +50 %).
 #include "ocm_common.cuh"
 
+#include <atomic>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -95,8 +96,6 @@ constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
 
-__device__ unsigned int g_tc_timeout = 0;
-
 // ---------------------------------------------------------------- PTX wrappers ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -119,16 +118,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug must not hang the GPU; it raises a flag the host can read.
+// Bounded wait.  A hand-off that never completes (protocol bug, wedged TMA) must neither hang the GPU nor pass
+// unnoticed: after `max_polls` polls the waiting thread raises the CTA's abort word in shared memory and writes a code
+// into the device's status word (mapped host memory, runtime.cu).  Every role tests the abort word once per tile and
+// then stops working: the converters write NaN / reject for every row the CTA still owns (the tile in flight
+// included), the host reports OCM_ETIMEOUT at its next call.  The status word is cleared by the host when it reports,
+// so a later launch never inherits it.
 // (A/B-tested on the B200, twice: a leaner polling loop -- PTX loop around try_wait, 5 instructions per round -- is
 // 10 % SLOWER end to end than this one, try_wait suspend hints 6 % slower, and a __nanosleep back-off of 20..200 ns
 // makes no difference.  The loop stays as it is.)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+struct WaitCtx {
+    uint32_t abort_addr;        // shared-space address of the CTA's abort word
+    unsigned int* status;       // device-visible status word (may be NULL)
+    uint32_t max_polls;
+};
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
-        if ((spins & 0x3FFFu) == 0 && *reinterpret_cast<volatile unsigned int*>(&g_tc_timeout)) break;  // someone already gave up
-        if (spins > (1u << 20)) { atomicExch(&g_tc_timeout, 1u); break; }
+        if ((spins & 0xFFu) == 0 && lds32_volatile(w.abort_addr)) break;            // someone in this CTA already gave up
+        if (spins > w.max_polls) {
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(w.abort_addr), "r"(1u) : "memory");
+            if (w.status) atomicExch(w.status, 1u);
+            break;
+        }
     }
 }
 __device__ __forceinline__ ulonglong2 lds128(uint32_t addr) {
@@ -201,6 +219,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// named barrier that also ORs a predicate over its participants: the 512 converter threads take the abort decision
+// TOGETHER (a thread that skipped a tile on its own would leave the others at the tile's named barriers for ever)
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 q, %3, 0;\n\t"
+        "bar.red.or.pred p, %1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"(id), "r"(nthreads), "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+
 // packed fp32 pair arithmetic (sm_100 FADD2/FFMA2): one issue slot for two lanes of work
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(uint32_t lo, uint32_t hi) {
@@ -266,6 +297,9 @@ struct Args {
     const float* mu; const float* P; const float* Sinv;
     int A; int rule; float ct, cq, dlim;
     float* T2; float* Q; uint8_t* accept;
+    unsigned int* status;     // protocol status word (mapped host memory), see mbar_wait
+    uint32_t max_polls;       // bound of every mbarrier wait
+    int inject;               // test hook: CTA 0 drops one TMA stage of its first tile
 };
 
 // mbarrier slots
@@ -274,7 +308,7 @@ enum { B_FULL = 0, B_EMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AFREE = 2 * NSTAGE 
 
 static_assert(NACC_MAIN == 4 && STAGE_COLS / 16 == NACC_MAIN, "one D1 accumulator per k-step of a stage");
 static_assert(NABUF == 2 && P_MAX % D2_COLS == 0, "two A buffers; residual chunks of 128 columns");
-static_assert(8 * B_COUNT + 8 <= 256, "barrier block");
+static_assert(8 * B_COUNT + 8 <= 256, "barrier block (+ TMEM base word + abort word)");
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -295,6 +329,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + (uint32_t)SM_OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const WaitCtx wctx{bar0 + 8u * (uint32_t)B_COUNT + 4u, a.status, a.max_polls};
+    auto aborted = [&]() { return lds32_volatile(wctx.abort_addr) != 0u; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (a.n + TILE_M - 1) / TILE_M;
@@ -307,6 +343,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
+        s_tmem[1] = 0u;                                                    // abort word
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), NCONV); }
         for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), NMMAW); }
         for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFREE + b), NCONV); mbar_init(BAR(B_DREADY + b), 1); }
@@ -363,7 +400,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     tc_fence_after();
     // The CTA is alone on its SM (shared-memory footprint) and allocates all 512 columns, so the base is 0; using
     // the constant keeps every TMEM address an immediate in the MMA issue loop.  Anything else is flagged.
-    if (*s_tmem != 0u && tid == 0) atomicExch(&g_tc_timeout, 2u);
+    if (*s_tmem != 0u) {                                                   // uniform over the CTA: nothing below would be valid
+        if (tid == 0) { s_tmem[1] = 2u; if (a.status) atomicExch(a.status, 2u); }
+        __syncthreads();
+    }
     constexpr uint32_t tmem = 0u;
 
     if (warp < NCONV / 32) {
@@ -397,7 +437,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 
         // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
         auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
-            mbar_wait(bar_full, ring_phase);
+            mbar_wait(bar_full, ring_phase, wctx);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const ulonglong2 v = lds128(st + xo[i]);
@@ -411,6 +451,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         };
 
         for (int64_t k = 0; k < my_tiles; ++k) {
+            if (named_bar_or(2, NCONV, aborted())) {
+                // the CTA's protocol is dead: every row it still owns is marked, nothing else is touched
+                if (qd == 0) {
+                    const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
+                    if (grow < a.n) {
+                        if (a.T2) a.T2[grow] = __int_as_float(0x7fc00000);
+                        if (a.Q) a.Q[grow] = __int_as_float(0x7fc00000);
+                        if (a.accept) a.accept[grow] = 0;
+                    }
+                }
+                continue;
+            }
             const uint32_t kpar = (uint32_t)(k & 1);
             // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
             uint32_t mu_addr = mu0;
@@ -421,7 +473,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     f32x2 xc[QCOLS / 2];
                     load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
-                    mbar_wait(BAR(B_AFREE + b), aph ^ 1u);                  // MMAs of the buffer's previous user retired
+                    mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx);                  // MMAs of the buffer's previous user retired
                     tc_fence_after();
                     uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
@@ -440,7 +492,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             }
             {
             // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
-            mbar_wait(BAR(B_TREADY), kpar);
+            mbar_wait(BAR(B_TREADY), kpar, wctx);
             tc_fence_after();
             if (qd == 0) {
                 float t[16];
@@ -514,7 +566,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
                     if (sub == 0) {
-                        mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u);    // the chunk's six MMAs have retired
+                        mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u, wctx);    // the chunk's six MMAs have retired
                         dph ^= 1u << b;
                         tc_fence_after();
                     }
@@ -540,14 +592,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             {
             // combine the four column quarters of each spectrum, decide, write back
             if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
-            named_bar_sync(2, NCONV);
+            const bool dead = named_bar_or(2, NCONV, aborted());   // a wait of this tile gave up: none of its numbers is to be trusted
             if (qd == 0) {
                 const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
                 if (grow < a.n) {
-                    const float qq = (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
-                    if (a.T2) a.T2[grow] = t2_row;
+                    const float qq = dead ? __int_as_float(0x7fc00000) : (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
+                    const float tt = dead ? __int_as_float(0x7fc00000) : t2_row;
+                    if (a.T2) a.T2[grow] = tt;
                     if (a.Q) a.Q[grow] = qq;
-                    if (a.accept) a.accept[grow] = rule_distance(a.rule, t2_row * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
+                    if (a.accept) a.accept[grow] = (!dead && rule_distance(a.rule, tt * a.ct, qq * a.cq) < a.dlim) ? 1 : 0;
                 }
             }
             named_bar_sync(2, NCONV);                         // s_q reusable
@@ -564,15 +617,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             int slot = 0;
             uint32_t ring_phase = 0;
             for (int64_t k = 0; k < my_tiles; ++k) {
+                if (aborted()) break;
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
                 for (int w = 0; w < 2 * ns; ++w) {
                     const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
-                    mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1);           // all converters drained the slot
+                    mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx);           // all converters drained the slot
                     mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
                     const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
                     const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
-                    tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
-                    tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
+                    if (!(a.inject && blockIdx.x == 0 && k == 0 && w == 3)) {       // test hook: that stage never arrives
+                        tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
+                        tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
+                    }
                     if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
                 }
             }
@@ -595,13 +651,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         uint32_t aph = 0, dph = 0;          // running phase of the A buffers (pairwise) and of MY residual buffer
         for (int64_t k = 0; k < my_tiles; ++k) {
+            if (aborted()) break;
             // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
             uint32_t patom = sP;
 #pragma unroll 1
             for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    mbar_wait(BAR(B_AFULL + b), aph);
+                    mbar_wait(BAR(B_AFULL + b), aph, wctx);
                     tc_fence_after();
                     // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
                     // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
@@ -623,11 +680,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             }
             tc_commit_elect(BAR(B_TREADY));
             // ---- reconstruction: D = T * P (chunks with buffer b == mw) -----------------------------
-            mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1));
+            mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1), wctx);
             tc_fence_after();
 #pragma unroll 1
             for (int c2 = mw; c2 < nc; c2 += NMMAW) {
-                mbar_wait(BAR(B_DFREE + mw), dph ^ 1u);                     // every converter has read the buffer's previous chunk
+                mbar_wait(BAR(B_DFREE + mw), dph ^ 1u, wctx);                     // every converter has read the buffer's previous chunk
                 dph ^= 1u;
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
@@ -643,6 +700,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     }
 
     // ---- teardown -----------------------------------------------------------------------------
+    if (aborted()) {            // in-flight TMA boxes and MMAs of the abandoned tile: give them time to land
+        for (int i = 0; i < 100; ++i) __nanosleep(2000);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA) {
@@ -685,6 +745,8 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, i
 }  // namespace tc
 }  // namespace ocm
 
+static std::atomic<int> g_inject_polls{0};     // test hook, see ocm_simca_score_tc_inject_stall
+
 // Shape gate of the dispatcher: fp32 rows of 1024 wavelengths, n_components <= 16, 16-byte aligned rows, no fused
 // SNV, and enough rows to fill the machine (below ~2 tiles per SM the FP32-pipe kernels have less fixed cost:
 // this kernel stages 96 KB of loadings per CTA).  OCM_DISABLE_TC=1 forces the FP32-pipe kernels (A/B runs).
@@ -711,7 +773,11 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     CUtensorMap tmap;
     int rc = tc::make_tensor_map(&tmap, X, n, p, ldx);
     if (rc) return rc;
-    tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept};
+    rc = tc_status_report("ocm_simca_score_tc_f32");          // an EARLIER launch gave up: say so before doing more work
+    if (rc) return rc;
+    const int inject = g_inject_polls.exchange(0);
+    tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0};
     auto kern = tc::score_tc_kernel;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
@@ -721,10 +787,14 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     return check_launch("score_tc_kernel");
 }
 
-// 0 = no protocol timeout seen so far (synchronises the device; debugging / tests only)
+// synchronise, then read AND clear the protocol status word of the tcgen05 kernels (0 = clean)
 extern "C" int ocm_simca_score_tc_status(void) {
-    unsigned int v = 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(&v, ocm::tc::g_tc_timeout, sizeof(v)) != cudaSuccess) return -1;
-    return (int)v;
+    return ocm::tc_status_take();
+}
+
+extern "C" int ocm_simca_score_tc_inject_stall(int32_t max_polls) {
+    OCM_REQUIRE(max_polls >= 16, OCM_EINVAL, "max_polls must be >= 16");
+    g_inject_polls.store(max_polls);
+    return 0;
 }

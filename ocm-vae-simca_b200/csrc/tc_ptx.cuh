@@ -31,14 +31,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait.  A hand-off that never completes is a protocol bug (or a wedged TMA); it must neither hang the
-// GPU nor go unnoticed: after ~2^26 polls (seconds) the kernel traps, the launch fails with a CUDA error and the
-// C-ABI wrapper reports it.
-__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
+// Bounded wait.  A hand-off that never completes is a protocol bug (or a wedged TMA); it must neither hang the GPU
+// nor go unnoticed, and it must not raise a GPU fault either: after `max_polls` polls the waiting thread raises the
+// CTA's abort word in shared memory and writes a code into the device's status word (mapped host memory,
+// runtime.cu); the roles of the CTA see the abort word, stop, and mark everything the CTA owns as NaN; the host
+// reports OCM_ETIMEOUT at its next call.  Returns false when the wait was abandoned.
+struct WaitCtx {
+    uint32_t abort_addr;        // shared-space address of the CTA's abort word
+    unsigned int* status;       // device-visible status word (may be NULL)
+    uint32_t max_polls;
+};
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, const WaitCtx& w, uint32_t code) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        ++spins;
+        if ((spins & 0xFFu) == 0 && lds32_volatile(w.abort_addr)) return false;
+        if (spins > w.max_polls) {
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(w.abort_addr), "r"(code) : "memory");
+            if (w.status) atomicExch(w.status, code);
+            return false;
+        }
     }
+    return true;
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -5,7 +5,8 @@ one small payload: the partial Gram (p x p fp64), column sums and row count are 
 with an NCCL all-reduce over NVLink (`engine.covariance(..., group=...)`); every rank then
 finalises covariance + eigensolve redundantly.  CV folds are dealt round-robin to ranks and
 the per-(fold, A) confusion counts are all-gathered.  The same code runs on `gloo` for the
-CPU tests of the host logic (tests/test_dist_gloo.py).
+CPU tests of the host logic (tests/test_host_cpu.py::test_gloo_world2_moment_allreduce) and for the GPU test
+that runs two ranks on one device (tests/test_gpu_parity.py::test_cv_grid_folds_over_ranks).
 """
 from __future__ import annotations
 

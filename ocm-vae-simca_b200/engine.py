@@ -232,29 +232,80 @@ def cov_from_parts(Gparts, sparts, counts, weights, shift):
     return Cm, mean
 
 
-def covariance(X, row_idx=None, group=None):
+class PhaseTimer:
+    """CUDA-event marks between the phases of a fit (bench.py's `fit` leg): mark(name) closes the phase `name`."""
+
+    def __init__(self):
+        torch = _torch()
+        self._ev = [("", torch.cuda.Event(enable_timing=True))]
+        self._ev[0][1].record()
+
+    def mark(self, name):
+        torch = _torch()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._ev.append((name, e))
+
+    def result(self):
+        torch = _torch()
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self._ev[:-1], self._ev[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+GRAM_TC_MIN_ROWS = 16384     # below this the FP64 tensor-pipe (DMMA) kernel is used: CV folds, configs 1 / 2
+GRAM_TC_PRODUCTS = 13        # digit products of the integer Gram: 16 exact / 13 (<= 2^-37) / 10 (<= 2^-28)
+
+
+def covariance(X, row_idx=None, group=None, gram_path="auto", products=None, timer=None):
     """Sample covariance (ddof=1) and column mean of the selected rows.
 
-    Two passes (both tiny next to scoring): column sums give a provisional mean that is
-    used as the shift of the Gram accumulation, so G - n*d*d^T never cancels.
-    With torch.distributed initialised and `group` given, the partial moments of the row
-    shards are all-reduced (NCCL over NVLink) before the combination."""
+    Column sums give a provisional mean that is used as the shift of the Gram accumulation, so G - n*d*d^T never
+    cancels.  Bulk fits (>= GRAM_TC_MIN_ROWS rows, `gram_path` "auto" or "tc") take the integer tcgen05
+    Gram (csrc/gram_tc.cu): one pass for sums / extrema, one pass that quantises and accumulates the exact column sums,
+    then int8 MMAs; small fits take the FP64 tensor-pipe kernel ("dmma").  With torch.distributed initialised and
+    `group` given, the partial moments of the row shards are all-reduced (NCCL over NVLink) before the combination."""
     torch = _torch()
-    s0, _, n = colstats(X, row_idx)
+    n_rows = X.shape[0] if row_idx is None else row_idx.numel()
+    use_tc = gram_path == "tc" or (gram_path == "auto" and n_rows >= GRAM_TC_MIN_ROWS)
+    if group is not None:
+        import torch.distributed as dist
+    mark = timer.mark if timer is not None else (lambda name: None)
+    if use_tc:
+        s0, mn, mx, n = colstats_minmax(X, row_idx)
+    else:
+        s0, _, n = colstats(X, row_idx)
+    mark("colstats")
     n_tot = torch.tensor([float(n)], dtype=torch.float64, device=X.device)
     if group is not None:
-        import torch.distributed as dist
         dist.all_reduce(s0, group=group)
         dist.all_reduce(n_tot, group=group)
+        mark("allreduce")
     shift = s0 / n_tot
-    G = gram(X, row_idx, shift)
-    s1, _, _ = colstats(X, row_idx, shift)
+    if use_tc:
+        G, s1, flags = gram_tc(X, row_idx, shift, mn, mx, products=products or GRAM_TC_PRODUCTS)
+    else:
+        G = gram(X, row_idx, shift)
+        s1, _, _ = colstats(X, row_idx, shift)
+        flags = None
+    mark("gram")
     if group is not None:
-        import torch.distributed as dist
         dist.all_reduce(G, group=group)
         dist.all_reduce(s1, group=group)
+        if flags is not None:
+            dist.all_reduce(flags, group=group)
+        mark("allreduce")
     N = int(round(float(n_tot.item())))
+    if flags is not None:
+        clamped, nonfinite = (int(v) for v in flags.cpu().tolist())
+        if clamped:
+            raise native.NativeError(f"integer Gram: {clamped} values exceeded the column bounds (internal error)")
+        if nonfinite:
+            G.fill_(float("nan"))          # what an IEEE accumulation of the same rows would have produced
     Cm, mean = cov_from_parts(G.unsqueeze(0), s1.unsqueeze(0), [N], [1.0], shift)
+    mark("covariance")
     return Cm, mean, N
 
 
@@ -409,7 +460,7 @@ def _full_spectrum(Cm, n, p):
     return eigs
 
 
-def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False) -> PCAModel:
+def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False, gram_path="auto", products=None, timer=None) -> PCAModel:
     """PCA of the selected rows: mean, k leading loadings (sign-normalised rows) and the eigenvalue spectrum.
 
     Default: block subspace iteration for the k leading pairs + traces of the deflated covariance for the tail sums
@@ -417,10 +468,12 @@ def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False) -> PCAModel:
     if the whole array is asked for.  `full_spectrum=True` (or a subspace iteration that did not converge: flat
     spectrum at k) takes the full symmetric eigensolve straight away."""
     from .limits import LazySpectrum
-    Cm, mean, n = covariance(X, row_idx, group)
+    Cm, mean, n = covariance(X, row_idx, group, gram_path=gram_path, products=products, timer=timer)
     p = X.shape[1]
     if not full_spectrum and k < p:
         w, V, tails, conv = eig_topk_subspace(Cm.unsqueeze(0), k, tol=1e-13, max_iter=90)
+        if timer is not None:
+            timer.mark("eigensolve")
         if bool(conv[0]):
             P = V[0, :, :k].transpose(0, 1).contiguous()
             sign_normalise_(P)

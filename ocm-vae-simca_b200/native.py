@@ -114,6 +114,7 @@ SIGNATURES = {
     "ocm_simca_score_tc_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                          _vp, _vp, _vp, _vp]),
     "ocm_simca_score_tc_status": (C.c_int, []),
+    "ocm_simca_score_tc_inject_stall": (C.c_int, [_i32]),
     "ocm_simca_host_release": (C.c_int, []),
     "ocm_simca_score_tc_supported": (C.c_int, [_i64, _i32, _i64, _i32, _i32, _vp]),
     "ocm_simca_score_f64in": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),

@@ -165,6 +165,7 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
         prm = eff_params(combo)
         cols = torch.as_tensor(np.asarray(lvs) - 1, device=Xd.device)
         pooled = torch.zeros((n_samples, len(lvs)), dtype=torch.uint8, device=Xd.device)
+        writer = torch.zeros((n_samples, len(lvs)), dtype=torch.int32, device=Xd.device) if world > 1 else None
         cnt_folds = torch.zeros((n_folds, len(lvs), 4), dtype=torch.int64, device=Xd.device)
         for fi, f in zip(mine, fm.folds):
             # limits of every requested nested model of this fold (host scalars), then ONE launch
@@ -181,12 +182,17 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
                                             ct=ct, cq=cq, dlim=dl)
             acc = acc.index_select(1, cols).contiguous()
             pooled[f["te_idx"]] = acc
+            if writer is not None:
+                writer[f["te_idx"]] = acc.to(torch.int32) + 2 * (fi + 1)
             cnt_folds[fi] = engine.conformity_counts(acc, f["is_target"])
         if world > 1:
-            pooled32 = pooled.to(torch.int32)                  # test rows are disjoint over folds: the sum is a merge
-            tdist.all_reduce(pooled32, group=group)
+            # A row can sit in the test set of SEVERAL folds (ClasswiseKFoldWithExternalVal puts every non-target row
+            # in all of them); the reference keeps the decision of the LAST fold that tested it (pred_vec[te] = y_pred,
+            # CVSIMCA.py:186).  Every rank tags its decisions with 2 * (fold + 1); the maximum over the ranks is the
+            # last writer, its low bit the decision (0 = never tested).
+            tdist.all_reduce(writer, op=tdist.ReduceOp.MAX, group=group)
             tdist.all_reduce(cnt_folds, group=group)
-            pooled = pooled32.to(torch.uint8)
+            pooled = (writer & 1).to(torch.uint8)
         cnt = cnt_folds.cpu().numpy()
         spec_folds = np.stack([_percent_metrics(cnt[fi, :, 0], cnt[fi, :, 1], cnt[fi, :, 2], cnt[fi, :, 3])[1]
                                for fi in range(n_folds)])

@@ -27,7 +27,9 @@ def exact_quantised_gram(X, shift, mn, mx, products):
             if k + l >= dmin:
                 G += (d[k].astype(np.float64).T @ d[l].astype(np.float64)).astype(np.longdouble) * np.longdouble(256.0) ** (k + l)
     inv = np.ldexp(1.0, -sc).astype(np.longdouble)
-    return np.asarray(G * inv[:, None] * inv[None, :], dtype=np.float64), (v.sum(0) * np.ldexp(1.0, -sc))
+    Gq = np.asarray(G * inv[:, None] * inv[None, :], dtype=np.float64)
+    np.fill_diagonal(Gq, np.asarray((v.astype(np.longdouble) ** 2).sum(0) * inv * inv, dtype=np.float64))   # exact diagonal
+    return Gq, (v.sum(0) * np.ldexp(1.0, -sc))
 
 
 def check(n, p, dtype, products, gather=False, seed=0):
