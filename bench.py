@@ -14,6 +14,8 @@ Extra keys beyond the base contract: `roofline`, `cpu_baseline`, `e2e`, `clocks`
   `strong` -- the same 10 M rows in TOTAL split over the N GPUs (configs[2] read as strong scaling),
   `fit`    -- BASELINE configs[3]: row-sharded PCA fit (column statistics, integer tcgen05 Gram, NCCL all-reduce of the
               partial moments, eigensolve) at 2 M x 2048 rows per GPU, tensor roofline,
+  `vae`    -- BASELINE configs[4]: ConvVAE1D (latent 16) bf16 DDP training step + row-sharded fused latent-T2 /
+              reconstruction-Q scoring of 1 M x 1024 spectra,
   `cv`     -- BASELINE.json's second metric: CVSIMCA fits/s on configs[1].
 The CPU arms time the UNMODIFIED reference staged in baseline/_ref (kind "reference"); when that directory is absent
 (nothing staged) they fall back to the oracle's restatement (kind "port").
@@ -59,6 +61,8 @@ def parse():
     ap.add_argument("--fit-rows", type=int, default=2_000_000, help="rows per GPU of the PCA-fit leg")
     ap.add_argument("--fit-p", type=int, default=2048)
     ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--vae-rows", type=int, default=1_000_000, help="rows in TOTAL of the VAE-SIMCA leg (configs[4])")
+    ap.add_argument("--no-vae", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-cv", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -414,6 +418,129 @@ def cv_leg(device, group=None, rank=0, world=1):
     return out
 
 
+def vae_leg(args, device, group, rank, world, local_rank):
+    """BASELINE configs[4]: VAE-SIMCA on 1 M x 1024 spectra (latent 16), rows sharded over the GPUs.
+    (a) training: ConvVAE1D (the reference architecture, /root/reference/vae_model.py:6-129, 17 M parameters) under
+        DistributedDataParallel, bf16 autocast, fused Adam, cosine beta-VAE loss (vae_bce_nut.py:178-192 trains in fp32
+        at batch 512, one GPU); the step time includes the NCCL gradient all-reduce;
+    (b) scoring: one encoder pass + deterministic decode per batch in bf16, then ONE fused kernel per batch
+        (ocm_latent_score_f32: latent T2 against the calibration mean / covariance + reconstruction Q from the bf16
+        reconstruction), the whole shard per step (final_vaesimca.py:471-533 does this with a double forward pass and
+        per-batch numpy on the host)."""
+    import torch
+    from ocm_vae_simca_b200 import dist as odist
+    from ocm_vae_simca_b200 import engine, native, synth
+    from ocm_vae_simca_b200.vae import ConvVAE1D
+    from ocm_vae_simca_b200.vae.convvae import beta_vae_cosine_loss
+    from ocm_vae_simca_b200.vae.vae_simca import latent_recon_scores
+    L, d, rows_total = 1024, 16, args.vae_rows
+    lo, hi = odist.shard_rows(rows_total, rank, world)
+    n = hi - lo
+    X = synth.make_spectra_device(n, L, device, seed=3000 + rank)
+    mean = X[:65536].mean(0); std = X[:65536].std(0) + 1e-8
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(mean, group=group); mean /= world
+        dist.all_reduce(std, group=group); std /= world
+    torch.manual_seed(0)
+    vae = ConvVAE1D(L, d, mean.cpu().numpy(), std.cpu().numpy()).to(device)
+    model = vae
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(vae, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(vae.parameters(), lr=1e-3, fused=True)
+    Bt = 4096
+
+    def train_step(i):
+        xb = X[(i * Bt) % (n - Bt):][:Bt]
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            xr, mu_, lv_ = model(xb)
+            loss = beta_vae_cosine_loss(xb, xr.float(), mu_.float(), lv_.float(), as_floats=False)[0]
+        loss.backward()
+        opt.step()
+        return loss
+    vae.train()
+    for i in range(3):
+        train_step(i)
+    torch.cuda.synchronize()
+    if group is not None:
+        dist.barrier()
+    tsteps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(tsteps):
+        loss = train_step(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    train_ms = odist.max_over_ranks(e0.elapsed_time(e1), device) / tsteps
+    final_loss = float(loss)
+
+    # calibration statistics of the latent means (VAE_SIMCA.py:245-248), all-reduced over the shards
+    vae.eval()
+    Bs = 8192
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        mu_cal = torch.cat([vae.encode((X[r:r + Bs] - vae.spec_mean) / vae.spec_std)[0].float() for r in range(0, min(n, 65536), Bs)])
+    cnt = torch.tensor([float(mu_cal.shape[0])], dtype=torch.float64, device=device)
+    s1 = mu_cal.double().sum(0); s2 = mu_cal.double().T @ mu_cal.double()
+    if group is not None:
+        for t in (cnt, s1, s2):
+            dist.all_reduce(t, group=group)
+    m = s1 / cnt
+    cov = (s2 - cnt * torch.outer(m, m)) / (cnt - 1) + 1e-6 * torch.eye(d, dtype=torch.float64, device=device)
+    vae.latent_mean.copy_(m.float()); vae.latent_cov_inv.copy_(torch.linalg.inv(cov).float())
+
+    d2_all = torch.empty(n, device=device); q_all = torch.empty(n, device=device)
+
+    def score_pass():
+        for r in range(0, n, Bs):
+            xb = X[r:r + Bs]
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                d2, q, _ = latent_recon_scores(vae, xb, sample=False, recon_dtype=torch.bfloat16)
+            d2_all[r:r + xb.shape[0]] = d2; q_all[r:r + xb.shape[0]] = q
+    score_pass()
+    torch.cuda.synchronize()
+    if group is not None:
+        dist.barrier()
+    l0 = native.launch_count()
+    e0.record()
+    score_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = native.launch_count() - l0
+    score_ms = odist.max_over_ranks(e0.elapsed_time(e1), device)
+
+    # the fused epilogue alone on resident tensors of one pass worth of rows (its HBM roofline)
+    ne = min(n, 262144)
+    z = torch.randn(ne, d, device=device); xr = X[:ne].to(torch.bfloat16)
+    for _ in range(2):
+        engine.latent_score(z=z, m=vae.latent_mean, Sinv=vae.latent_cov_inv, x=X[:ne], xrec=xr)
+    e0.record()
+    for _ in range(5):
+        engine.latent_score(z=z, m=vae.latent_mean, Sinv=vae.latent_cov_inv, x=X[:ne], xrec=xr)
+    e1.record()
+    torch.cuda.synchronize()
+    epi_ms = e0.elapsed_time(e1) / 5
+    epi_bytes = ne * (4 * L + 2 * L + 4 * d + 8)
+    acc_frac = float(((d2_all <= torch.quantile(d2_all[:100000], 0.95)) & (q_all <= torch.quantile(q_all[:100000], 0.95))).float().mean())
+    del X
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    hbm, _ = measured_peak()
+    return {"metric": "VAE-SIMCA spectra/s (ConvVAE1D latent 16, bf16)", "n_gpus": world, "rows_total": rows_total, "rows_per_gpu": n,
+            "scaling": "strong (1 M rows in total, sharded)",
+            "scoring": {"value": rows_total / (score_ms * 1e-3), "unit": "spectra/s", "ms_per_pass": score_ms, "batch": Bs,
+                        "what": "bf16 encoder + decoder (PyTorch cuDNN/cuBLAS) + fused latent T2 / reconstruction Q kernel, whole shard",
+                        "gpu_launches": int(launches), "accepted_frac_p95_rule": acc_frac},
+            "training": {"value": world * Bt / (train_ms * 1e-3), "unit": "spectra/s", "ms_per_step": train_ms, "batch_per_gpu": Bt,
+                         "what": "DistributedDataParallel bf16-autocast step (fwd + bwd + NCCL gradient all-reduce + fused Adam)" if world > 1
+                                 else "bf16-autocast step (fwd + bwd + fused Adam)",
+                         "parameters": int(sum(p_.numel() for p_ in vae.parameters())), "loss_after": final_loss},
+            "epilogue_roofline": {"kernel": "latent_score_kernel<bf16 xrec>", "bound": "hbm", "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
+                                  "peak": hbm, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / hbm,
+                                  "algorithmic_bytes_per_launch": epi_bytes, "traffic": None}}
+
+
 def main():
     args = parse()
     from ocm_vae_simca_b200 import dist as odist
@@ -564,6 +691,12 @@ def main():
             fit_out = fit_leg(args, device, dist.group.WORLD if world > 1 else None, rank, world)
         except Exception as e:
             fit_out = {"error": repr(e)}
+    vae_out = None
+    if not args.no_vae:
+        try:
+            vae_out = vae_leg(args, device, dist.group.WORLD if world > 1 else None, rank, world, local_rank)
+        except Exception as e:
+            vae_out = {"error": repr(e)}
     cv_out = None
     if not args.no_cv:
         try:
@@ -601,6 +734,8 @@ def main():
         line["strong"] = strong
     if fit_out is not None:
         line["fit"] = fit_out
+    if vae_out is not None:
+        line["vae"] = vae_out
     if cv_out is not None:
         line["cv"] = cv_out
     print(json.dumps(line), flush=True)

@@ -133,6 +133,28 @@ int ocm_cov_from_parts_f64(const double* Gparts, const double* sparts, const int
  * fits all CV folds at once (replaces the per-(fold, LV) SVDs of utils/CVSIMCA.py:183-184). */
 int ocm_eigh_small_f64(const double* H, int32_t m, int32_t batch, double* evals, double* evecs, void* stream);
 
+/* ---- a4 / a12: steps of the batched block subspace iteration that yields the k leading eigenpairs of the covariance
+ * (the loadings: Vt of the SVD at utils/SIMCA.py:64,:75) and the eigenvalue tail sums of utils/SIMCA.py:189-205.
+ * Row-major fp64; C [batch][p][p] symmetric; blocks [batch][p][kb], kb <= 64 (csrc/eig_sub.cu).
+ *   symm_mul:       Z = C Q                                   (FP64 tensor pipe)
+ *   tn_small:       H = A^T B, [batch][ka][kb]
+ *   chol_solve:     L = chol(sym(G)) lower, Y <- Y L^-T in place; info[b] = 0 or the 1-based index of a non-positive pivot
+ *   mul_small:      Y = Z U, U [batch][kb][ku]
+ *   ritz_residual:  res2[b][c] = sum_rows (ZU[row][c] - X[row][c] w[b][c])^2
+ *   tail_sums:      R = C - sum_{a<k} w_a x_a x_a^T (written to R), R2 = upper triangle of R^2 (scratch),
+ *                   tails[b] = {tr R, |R|_F^2, tr R^3} */
+int ocm_eig_symm_mul_f64(const double* C, const double* Q, double* Z, int32_t p, int32_t kb, int32_t batch, void* stream);
+int ocm_eig_tn_small_f64(const double* A, const double* B, double* H, int32_t p, int32_t ka, int32_t kb,
+                         int32_t batch, void* stream);
+int ocm_eig_chol_solve_f64(const double* G, double* Y, double* L, int32_t* info, int32_t p, int32_t kb,
+                           int32_t batch, void* stream);
+int ocm_eig_mul_small_f64(const double* Z, const double* U, double* Y, int32_t p, int32_t kb, int32_t ku,
+                          int32_t batch, void* stream);
+int ocm_eig_ritz_residual_f64(const double* ZU, const double* X, const double* w, double* res2, int32_t p,
+                              int32_t kb, int32_t batch, void* stream);
+int ocm_eig_tail_sums_f64(const double* C, const double* X, const double* w, int32_t p, int32_t kb, int32_t k,
+                          int32_t batch, double* R, double* R2, double* tails, void* stream);
+
 /* ---- a5 / a9 / a10: fused scoring (replaces pca.transform + inverse_transform + the
  * two reductions of SIMCA.predict / SIMCA.transform, utils/SIMCA.py:101-145) -----------
  * For each row x:  [optional SNV] -> xc = x - mu -> t = P xc -> r = xc - P^T t ->

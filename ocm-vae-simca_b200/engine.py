@@ -348,19 +348,50 @@ def eigh_small(H):
     return w, U
 
 
-def _orthonormalise(Z):
-    """Batched tall-skinny orthonormalisation [F, p, kb] by Cholesky-QR applied twice (two small Gram products, two
-    kb x kb Cholesky factorisations, two triangular solves: ~0.3 ms where the batched Householder QR takes 2.3 ms at
-    10 x 1050 x 32).  CholQR2 is orthogonal to machine precision while cond(Z)^2 * eps < 1; if a factorisation
-    fails (rank-deficient block) fall back to Householder QR."""
+def _symm_mul(Cs, Q):
+    """Z = C Q for a batch of symmetric fp64 matrices (ocm_eig_symm_mul_f64: FP64 tensor pipe)."""
     torch = _torch()
-    Y = Z
+    F, p, kb = Q.shape
+    Z = torch.empty_like(Q)
+    native.check(native.lib().ocm_eig_symm_mul_f64(_p(Cs), _p(Q), _p(Z), p, kb, F, _stream()), "ocm_eig_symm_mul_f64")
+    return Z
+
+
+def _tn_small(A, B):
+    """H = A^T B, [F, ka, kb] (ocm_eig_tn_small_f64)."""
+    torch = _torch()
+    F, p, ka = A.shape
+    kb = B.shape[2]
+    H = torch.empty((F, ka, kb), dtype=torch.float64, device=A.device)
+    native.check(native.lib().ocm_eig_tn_small_f64(_p(A), _p(B), _p(H), p, ka, kb, F, _stream()), "ocm_eig_tn_small_f64")
+    return H
+
+
+def _mul_small(Z, U):
+    """Y = Z U, [F, p, kb] x [F, kb, ku] (ocm_eig_mul_small_f64)."""
+    torch = _torch()
+    F, p, kb = Z.shape
+    ku = U.shape[2]
+    Y = torch.empty((F, p, ku), dtype=torch.float64, device=Z.device)
+    native.check(native.lib().ocm_eig_mul_small_f64(_p(Z), _p(U.contiguous()), _p(Y), p, kb, ku, F, _stream()), "ocm_eig_mul_small_f64")
+    return Y
+
+
+def _orthonormalise(Z, fail):
+    """Batched tall-skinny orthonormalisation [F, p, kb] by Cholesky-QR applied twice, in the library's own kernels: two
+    small Gram products (ocm_eig_tn_small_f64), two in-CTA kb x kb Cholesky factorisations and row-wise triangular solves
+    (ocm_eig_chol_solve_f64).  CholQR2 is orthogonal to machine precision while cond(Z)^2 * eps < 1; a factorisation that
+    meets a non-positive pivot (rank-deficient block) is recorded in `fail` [F] (int32, accumulated on the device, read by
+    the caller at its next synchronisation) and that matrix goes to the full solver."""
+    torch = _torch()
+    F, p, kb = Z.shape
+    Y = Z.contiguous().clone()
+    L = torch.empty((F, kb, kb), dtype=torch.float64, device=Z.device)
+    info = torch.empty(F, dtype=torch.int32, device=Z.device)
     for _ in range(2):
-        G = Y.transpose(1, 2) @ Y
-        L, info = torch.linalg.cholesky_ex(G)
-        if bool((info != 0).any()):
-            return torch.linalg.qr(Z)[0]
-        Y = torch.linalg.solve_triangular(L, Y.transpose(1, 2), upper=False).transpose(1, 2)
+        G = _tn_small(Y, Y)
+        native.check(native.lib().ocm_eig_chol_solve_f64(_p(G), _p(Y), _p(L), _p(info), p, kb, F, _stream()), "ocm_eig_chol_solve_f64")
+        fail |= info != 0
     return Y
 
 
@@ -370,43 +401,51 @@ def eig_topk_subspace(Cs, k_need, tol=1e-11, max_iter=60, seed=0):
 
     This is what the CV grid needs per fold (loadings up to A_max, eigenvalues up to A_max, theta_1..3 of the rest for
     the Jackson-Mudholkar / chi2box / ci limits) without a full eigensolve per fold -- ten 1050 x 1050 fp64 `eigh`
-    calls were 90 % of the grid's wall time.  One batched product C Q per iteration; a fold that has not converged
-    after `max_iter` (flat spectrum at A_max) is flagged so the caller can fall back to the full solver.
+    calls were 90 % of the grid's wall time.  Every numerical step is a kernel of this library (csrc/eig_sub.cu,
+    csrc/eig_small.cu, csrc/moments.cu); torch only allocates and draws the random start block.  One batched product
+    C Q per iteration; a matrix that has not converged after `max_iter` (flat spectrum at A_max) or whose block lost rank
+    is flagged so the caller can fall back to the full solver.
 
     Cs [F, p, p].  Returns (w [F, kb] descending Ritz values, X [F, p, kb] Ritz vectors, tails [F, 3] =
     sums of lambda, lambda^2, lambda^3 beyond the first k_need, converged [F] bool)."""
     torch = _torch()
+    lib = native.lib()
+    Cs = Cs.contiguous()
     F, p, _ = Cs.shape
-    kb = min(p, max(k_need + 12, 32))
+    kb = min(p, max(k_need + 12, 32), 64)
+    if k_need > kb:
+        raise ValueError("at most 64 leading eigenpairs are supported by the subspace solver")
     g = torch.Generator(device=Cs.device)
     g.manual_seed(seed)
-    Q = torch.linalg.qr(torch.randn((F, p, kb), generator=g, dtype=torch.float64, device=Cs.device))[0]
+    fail = torch.zeros(F, dtype=torch.bool, device=Cs.device)
+    Q = _orthonormalise(torch.randn((F, p, kb), generator=g, dtype=torch.float64, device=Cs.device), fail)
     conv = torch.zeros(F, dtype=torch.bool, device=Cs.device)
+    res2 = torch.empty((F, kb), dtype=torch.float64, device=Cs.device)
     w = X = None
     for it in range(max_iter):
-        Z = Cs @ Q
+        Z = _symm_mul(Cs, Q)
         if it % 3 != 2 and it != max_iter - 1:          # two plain power steps per Rayleigh-Ritz step
-            Q = _orthonormalise(Z)
+            Q = _orthonormalise(Z, fail)
             continue
-        H = Q.transpose(1, 2) @ Z
-        if kb <= 64:
-            w, U = eigh_small(H)                       # hand-written batched Jacobi (descending)
-        else:
-            w, U = torch.linalg.eigh(0.5 * (H + H.transpose(1, 2)))
-            w, U = w.flip(-1), U.flip(-1)
-        ZU = Z @ U
-        X = Q @ U
-        res = (ZU - X * w.unsqueeze(1)).norm(dim=1)                          # [F, kb] residual norms |C x - w x|
-        conv = res[:, :k_need].max(dim=1).values <= tol * w[:, 0]
-        if bool(conv.all()):
+        H = _tn_small(Q, Z)
+        w, U = eigh_small(H)                           # hand-written batched Jacobi (descending)
+        ZU = _mul_small(Z, U)
+        X = _mul_small(Q, U)
+        native.check(lib.ocm_eig_ritz_residual_f64(_p(ZU), _p(X), _p(w), _p(res2), p, kb, F, _stream()), "ocm_eig_ritz_residual_f64")
+        res = res2.sqrt()                                                    # [F, kb] residual norms |C x - w x|
+        conv = (res[:, :k_need].max(dim=1).values <= tol * w[:, 0]) & ~fail
+        if bool((conv | fail).all()):
             break
-        Q = _orthonormalise(ZU)
-    Xk = X[:, :, :k_need]
-    R = Cs - (Xk * w[:, :k_need].unsqueeze(1)) @ Xk.transpose(1, 2)          # deflated: no cancellation in the traces
-    t1 = R.diagonal(dim1=1, dim2=2).sum(-1)
-    t2 = (R * R).sum(dim=(1, 2))
-    t3 = ((R @ R) * R).sum(dim=(1, 2))
-    return w, X, torch.stack([t1, t2, t3], dim=1), conv
+        Q = _orthonormalise(ZU, fail)
+    conv = conv & ~fail
+    # tail power sums from the explicitly deflated matrix (no cancellation): R = C - X_k diag(w_k) X_k^T,
+    # tr R, |R|_F^2, tr R^3 = sum_ij (R^2)_ij R_ij with R^2 = R^T R from the FP64 tensor-pipe Gram kernel
+    R = torch.empty_like(Cs)
+    R2 = torch.empty_like(Cs)
+    tails = torch.empty((F, 3), dtype=torch.float64, device=Cs.device)
+    native.check(lib.ocm_eig_tail_sums_f64(_p(Cs), _p(X), _p(w), p, kb, int(k_need), F, _p(R), _p(R2), _p(tails), _stream()),
+                 "ocm_eig_tail_sums_f64")
+    return w, X, tails, conv
 
 
 @dataclass

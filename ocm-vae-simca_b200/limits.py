@@ -98,6 +98,44 @@ def tail_moments(eigs_all, A):
     return float(tail.sum()), float((tail ** 2).sum()), float((tail ** 3).sum())
 
 
+class DeviceSample:
+    """Training distances that stay on the GPU (bulk fits): the order statistics / moments the 'perc' and 'chi2pom'
+    limits need are reduced there (fp64), only scalars come back.  np.percentile's default (linear interpolation
+    between order statistics) is restated on the sorted device array."""
+
+    def __init__(self, values):
+        self.v = values                      # 1-D CUDA tensor (fp32 distances)
+
+    def __len__(self):
+        return int(self.v.numel())
+
+    def percentile(self, q):
+        import torch
+        srt = torch.sort(self.v.double()).values
+        pos = (q / 100.0) * (srt.numel() - 1)
+        lo = int(np.floor(pos)); hi = min(lo + 1, srt.numel() - 1)
+        a, b = float(srt[lo]), float(srt[hi])
+        return a + (b - a) * (pos - lo)
+
+    def mean(self):
+        return float(self.v.double().mean())
+
+    def var1(self):
+        return float(self.v.double().var(unbiased=True)) if self.v.numel() > 1 else 0.0
+
+
+def _percentile(x, q):
+    return x.percentile(q) if isinstance(x, DeviceSample) else float(np.percentile(x, q))
+
+
+def _mean(x):
+    return x.mean() if isinstance(x, DeviceSample) else float(np.mean(x))
+
+
+def _var1(x):
+    return x.var1() if isinstance(x, DeviceSample) else (float(np.var(x, ddof=1)) if len(x) > 1 else 0.0)
+
+
 def hotelling_limit(kind, cl, A, n, T2=None):
     """SIMCA.py:156-182.  Returns (limit, dof, scale); dof/scale only for 'chi2pom'."""
     if kind == "Fdist":
@@ -107,10 +145,10 @@ def hotelling_limit(kind, cl, A, n, T2=None):
     if kind == "chi2":
         return _chi2_ppf(cl, A), None, None
     if kind == "perc":
-        return float(np.percentile(T2, cl * 100)), None, None
+        return _percentile(T2, cl * 100), None, None
     if kind == "chi2pom":
-        h0 = float(np.mean(T2))
-        var = float(np.var(T2, ddof=1)) if len(T2) > 1 else 0.0
+        h0 = _mean(T2)
+        var = _var1(T2)
         dof = max(int(np.round(2 * h0 * h0 / var)) if var > 0 else 1, 1)
         return h0 * _chi2_ppf(cl, dof) / dof, dof, h0
     raise ValueError(f"unknown t2lim {kind!r}")
@@ -132,10 +170,10 @@ def residual_limit(kind, cl, thetas, Q=None, verbose=False):
             print(th1, th2, g, Ng)
         return float(g * stats.chi2.ppf(cl, Ng)), None, None
     if kind == "perc":
-        return float(np.percentile(Q, cl * 100)), None, None
+        return _percentile(Q, cl * 100), None, None
     if kind == "chi2pom":
-        v0 = float(np.mean(Q))
-        dof = max(round(2 * v0 * v0 / float(np.var(Q, ddof=1))), 1)
+        v0 = _mean(Q)
+        dof = max(round(2 * v0 * v0 / _var1(Q)), 1)
         return v0 * _chi2_ppf(cl, dof) / dof, dof, v0
     raise ValueError(f"unknown qlim {kind!r}")
 

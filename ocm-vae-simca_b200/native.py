@@ -103,6 +103,12 @@ SIGNATURES = {
     "ocm_gram_f64acc_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ocm_cov_from_parts_f64": (C.c_int, [_vp, _vp, C.POINTER(_i64), C.POINTER(C.c_double), _i32, _i32,
                                          _vp, _vp, _vp, _vp, _vp]),
+    "ocm_eig_symm_mul_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ocm_eig_tn_small_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ocm_eig_chol_solve_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ocm_eig_mul_small_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ocm_eig_ritz_residual_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ocm_eig_tail_sums_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ocm_eigh_small_f64": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "ocm_simca_score_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                       _vp, _vp, _vp, _vp, _vp]),

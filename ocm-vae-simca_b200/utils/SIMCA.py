@@ -54,24 +54,37 @@ class _DevicePCA:
 
 
 class _ModelDict(dict):
-    """`_model[cls]` of the reference (SIMCA.py:83-99) with one lazy entry: 'eigs_all' holds the leading eigenvalues and
-    the tail power sums the limits were computed from, and turns into the full eigenvalue array (one extra symmetric
-    eigenvalue solve) the first time it is read."""
+    """`_model[cls]` of the reference (SIMCA.py:83-99) with lazy entries.  'eigs_all' holds the leading eigenvalues and
+    the tail power sums the limits were computed from and turns into the full eigenvalue array (one extra symmetric
+    eigenvalue solve) the first time it is read; after a BULK fit the per-row arrays 'T', 'T2', 'Q', 'T2red', 'Qred'
+    are thunks too (the distances stay on the device, the scores are not computed at all until somebody asks)."""
 
-    def _materialise(self):
-        v = dict.get(self, "eigs_all")
-        if hasattr(v, "full"):
-            dict.__setitem__(self, "eigs_all", v.full())
+    def __init__(self, *a, lazy=None, **k):
+        super().__init__(*a, **k)
+        self._lazy = dict(lazy or {})
+
+    def _materialise(self, key=None):
+        keys = list(self._lazy) if key is None else ([key] if key in self._lazy else [])
+        for kk in keys:
+            dict.__setitem__(self, kk, self._lazy.pop(kk)())
+        if key in (None, "eigs_all"):
+            v = dict.get(self, "eigs_all")
+            if hasattr(v, "full"):
+                dict.__setitem__(self, "eigs_all", v.full())
 
     def __getitem__(self, key):
-        if key == "eigs_all":
-            self._materialise()
+        self._materialise(key)
         return dict.__getitem__(self, key)
 
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
     def get(self, key, default=None):
-        if key == "eigs_all":
-            self._materialise()
+        self._materialise(key)
         return dict.get(self, key, default)
+
+    def keys(self):
+        return list(dict.keys(self)) + list(self._lazy)
 
     def items(self):
         self._materialise()
@@ -84,6 +97,27 @@ class _ModelDict(dict):
     def copy(self):
         self._materialise()
         return _ModelDict(dict.copy(self))
+
+
+BULK_FIT_BYTES = 256 << 20     # class matrices above this take the bulk fit path (no copies, lazy per-row outputs)
+
+
+def _score_rows(Xd, idx, mean, P, Sinv, **kw):
+    """T2, Q, accept of the rows `idx` of Xd (None = all rows) through the dispatcher's bulk kernels; a row subset is
+    gathered in bounded chunks (<= 512 MB) instead of materialising the class matrix."""
+    torch = engine._torch()
+    if idx is None:
+        return engine.score(Xd, mean, P, Sinv, **kw)
+    n = int(idx.numel())
+    chunk = max(65536, (512 << 20) // (Xd.shape[1] * Xd.element_size()))
+    T2 = torch.empty(n, dtype=torch.float32, device=Xd.device)
+    Q = torch.empty(n, dtype=torch.float32, device=Xd.device)
+    acc = torch.empty(n, dtype=torch.uint8, device=Xd.device)
+    for r0 in range(0, n, chunk):
+        r1 = min(n, r0 + chunk)
+        t2, q, a = engine.score(Xd.index_select(0, idx[r0:r1]), mean, P, Sinv, **kw)
+        T2[r0:r1], Q[r0:r1], acc[r0:r1] = t2, q, a
+    return T2, Q, acc
 
 
 class SIMCA(BaseEstimator, ClassifierMixin):
@@ -134,9 +168,15 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         return self
 
     def _fit_one_class(self, Xd, rows, A):
-        """Device restatement of SIMCA.py:62-99."""
-        idx = engine.index_tensor(rows, Xd.device)
-        n = int(idx.numel())
+        """Device restatement of SIMCA.py:62-99.  Small class matrices keep every `_model[cls]` entry eager (scores T
+        included); above BULK_FIT_BYTES nothing is copied: the Gram runs through the gather index (or over all rows),
+        the training distances come from the bulk scoring kernel and stay on the device, 'perc' / 'chi2pom' limits
+        are reduced there, and the per-row entries of `_model[cls]` are produced on first access."""
+        import weakref
+        n_all = Xd.shape[0]
+        all_rows = rows.size == n_all and (rows.size == 0 or (rows[0] == 0 and rows[-1] == n_all - 1 and np.all(np.diff(rows) == 1)))
+        idx = None if all_rows else engine.index_tensor(rows, Xd.device)
+        n = int(rows.size)
         if not 1 <= A <= min(n - 1, Xd.shape[1], 64):
             raise ValueError(f"n_components={A} must be in 1..min(n_class-1, n_features, 64)")
         pca = engine.fit_pca(Xd, idx, A)
@@ -144,35 +184,53 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         torch = engine._torch()
         inv_eig = torch.as_tensor(1.0 / lam, device=Xd.device)
         Sinv = torch.diag(inv_eig)
-        Xcls = Xd.index_select(0, idx)
-        T2, Q, _, T = engine.score(Xcls, pca.mean, pca.P, Sinv, want_scores=True)
-        T2h = T2.double().cpu().numpy()
-        Qh = Q.double().cpu().numpy()
+        bulk = n * Xd.shape[1] * Xd.element_size() > BULK_FIT_BYTES
+        lazy = {}
+        if not bulk:
+            Xcls = Xd if idx is None else Xd.index_select(0, idx)
+            T2, Q, _, T = engine.score(Xcls, pca.mean, pca.P, Sinv, want_scores=True)
+            T2s = T2h = T2.double().cpu().numpy()
+            Qs = Qh = Q.double().cpu().numpy()
+            Th = T.double().cpu().numpy()
+        else:
+            T2, Q, _ = _score_rows(Xd, idx, pca.mean, pca.P, Sinv)
+            T2s, Qs = limits.DeviceSample(T2), limits.DeviceSample(Q)
+            T2h = Qh = Th = None
+            xref = weakref.ref(Xd)
+
+            def lazy_scores():
+                X_ = xref()
+                if X_ is None:
+                    raise RuntimeError("the training matrix of this bulk fit has been released; '_model[cls][\"T\"]' "
+                                       "can no longer be computed (read it while the data is alive, or refit)")
+                out = np.empty((n, A), dtype=np.float64)
+                chunk = max(65536, (256 << 20) // (X_.shape[1] * X_.element_size()))
+                for r0 in range(0, n, chunk):
+                    r1 = min(n, r0 + chunk)
+                    blk = X_[r0:r1] if idx is None else X_.index_select(0, idx[r0:r1])
+                    out[r0:r1] = engine.score(blk, pca.mean, pca.P, Sinv, want_scores=True)[3].double().cpu().numpy()
+                return out
+            lazy["T"] = lazy_scores
         lim = limits.all_limits(self.type, self.t2lim, self.t2cl, self.qlim, self.qcl, self.dcl, A, n,
-                                pca.eigs_all, T2h, Qh, verbose=True)
+                                pca.eigs_all, T2s, Qs, verbose=True)
         if self.type == 'dd':
             # the reference keeps these on the instance (last class wins, SIMCA.py:179-180,:215-216)
             self._t2dof, self._t2scfact = lim.t2dof, lim.t2scale
             self._qdof, self._qscfact = lim.qdof, lim.qscale
-            T2red, Qred = lim.t2dof * T2h / lim.t2scale, lim.qdof * Qh / lim.qscale
+            t2s, qs = lim.t2dof / lim.t2scale, lim.qdof / lim.qscale
         else:
             if self.t2lim == 'chi2pom':
                 self._t2dof, self._t2scfact = lim.t2dof, lim.t2scale
             if self.qlim == 'chi2pom':
                 self._qdof, self._qscfact = lim.qdof, lim.qscale
-            T2red, Qred = T2h / lim.T2_limit, Qh / lim.Q_limit
-        return _ModelDict({
+            t2s, qs = 1.0 / lim.T2_limit, 1.0 / lim.Q_limit
+        entries = {
             "pca_model": _DevicePCA(pca),
             "n_components": A,
             "xmean": pca.mean.cpu().numpy(),
             "invcovT": np.diag(1.0 / lam),
             "eigs_all": pca.eigs_all,
-            "T": T.double().cpu().numpy(),
             "P": pca.P.cpu().numpy(),
-            "T2": T2h,
-            "Q": Qh,
-            "T2red": T2red,
-            "Qred": Qred,
             "T2_limit": lim.T2_limit,
             "Q_limit": lim.Q_limit,
             "D_limit": lim.D_limit,
@@ -181,7 +239,20 @@ class SIMCA(BaseEstimator, ClassifierMixin):
             "_pca": pca,
             "_Sinv": Sinv,
             "_limits": lim,
-        })
+        }
+        if not bulk:
+            if self.type == 'dd':
+                T2red, Qred = lim.t2dof * T2h / lim.t2scale, lim.qdof * Qh / lim.qscale
+            else:
+                T2red, Qred = T2h / lim.T2_limit, Qh / lim.Q_limit
+            entries.update({"T": Th, "T2": T2h, "Q": Qh, "T2red": T2red, "Qred": Qred})
+        else:
+            entries.update({"_T2_device": T2, "_Q_device": Q})
+            lazy["T2"] = lambda: T2.double().cpu().numpy()
+            lazy["Q"] = lambda: Q.double().cpu().numpy()
+            lazy["T2red"] = lambda: T2.double().cpu().numpy() * t2s
+            lazy["Qred"] = lambda: Q.double().cpu().numpy() * qs
+        return _ModelDict(entries, lazy=lazy)
 
     # ------------------------------------------------------------------ scoring ---------
     def _score_class(self, Xd, cls, snv=False):

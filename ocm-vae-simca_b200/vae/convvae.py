@@ -78,6 +78,18 @@ class ConvVAE1D(nn.Module):
         self.register_buffer("latent_cov_inv", torch.eye(latent_dim))
         self._init_weights()
 
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """Checkpoints of the reference's other VAE script (utils/final_vaesimca.py:96 registers ONE buffer called
+        `q_threshold` and saves `model.state_dict()`): map it onto `threshold_q` and let the threshold buffers that
+        script never had keep their defaults, so that both families of reference checkpoints load with strict=True."""
+        old = prefix + "q_threshold"
+        if old in state_dict:
+            state_dict[prefix + "threshold_q"] = state_dict.pop(old)
+        for name in ("threshold", "threshold_q", "threshold_h", "threshold_f", "latent_mean", "latent_cov_inv"):
+            if prefix + name not in state_dict:
+                state_dict[prefix + name] = getattr(self, name).detach().clone()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
     def _init_weights(self):
         for m in self.modules():
             if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d, nn.Linear)):
@@ -110,12 +122,15 @@ class ConvVAE1D(nn.Module):
         return self.decode(z) * self.spec_std + self.spec_mean, mu, logvar
 
 
-def beta_vae_cosine_loss(x, x_recon, mu, logvar, beta=1.0, eps=1e-8):
-    """Chord-distance reconstruction + beta*KL (reference vae_model.py:136-145)."""
+def beta_vae_cosine_loss(x, x_recon, mu, logvar, beta=1.0, eps=1e-8, as_floats=True):
+    """Chord-distance reconstruction + beta*KL (reference vae_model.py:136-145).  `as_floats=False` returns the two
+    monitoring terms as device tensors (the reference's `.cpu().item()` is two host synchronisations per step)."""
     cos = F.cosine_similarity(x.flatten(1), x_recon.flatten(1), dim=1, eps=1e-12)
     cos = cos.clamp(-1.0 + eps, 1.0 - eps)
     rec = torch.sqrt(2.0 * (1.0 - cos)).mean()
     kl = -0.5 * (1 + logvar - mu.pow(2) - logvar.exp()).sum(1).mean()
+    if not as_floats:
+        return rec + beta * kl, rec.detach(), kl.detach()
     return rec + beta * kl, rec.detach().cpu().item(), kl.detach().cpu().item()
 
 

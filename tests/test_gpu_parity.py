@@ -308,6 +308,100 @@ def test_gram_tensor_core_exact(torch):
     assert flags.cpu().tolist()[1] == 1
 
 
+def test_bulk_fit_path(torch):
+    """SIMCA.fit above BULK_FIT_BYTES: no copy of the class rows, training distances from the bulk
+    scoring kernel kept on the device, 'perc' / 'chi2pom' limits reduced there, per-row `_model[cls]` entries lazy.
+    Same model as the eager path on the same rows; peak device memory stays close to the input."""
+    from ocm_vae_simca_b200.utils import SIMCA as simca_mod
+    import sys
+    S = sys.modules[SIMCA.__module__]
+    dev = torch.device("cuda")
+    X = synth.make_spectra_device(120_000, 256, dev, seed=12)
+    y = np.zeros(X.shape[0], dtype=np.int64); y[::7] = 1
+    old = S.BULK_FIT_BYTES
+    try:
+        for kw in (dict(), dict(t2lim="perc", qlim="perc"), dict(type="dd"), dict(model_class=[0, 1], n_components=[6, 3])):
+            kw = dict(dict(n_components=6, model_class=0, verbose=False), **kw)
+            S.BULK_FIT_BYTES = 1 << 62
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                eager = SIMCA(**kw).fit(X, y)
+                S.BULK_FIT_BYTES = 0
+                bulk = SIMCA(**kw).fit(X, y)
+            for cls in eager.model_class:
+                e, b = eager._model[cls], bulk._model[cls]
+                assert "T" in b and "_T2_device" in b and b["_T2_device"].is_cuda
+                for k in ("T2_limit", "Q_limit", "D_limit"):
+                    np.testing.assert_allclose(b[k], e[k], rtol=2e-6, err_msg=f"{kw} {k}")
+                np.testing.assert_allclose(b["T2"], e["T2"], rtol=3e-5)
+                np.testing.assert_allclose(b["Q"], e["Q"], rtol=3e-5)
+                np.testing.assert_allclose(b["T2red"], e["T2red"], rtol=3e-5)
+                np.testing.assert_allclose(np.abs(b["T"]), np.abs(e["T"]), rtol=1e-4, atol=1e-6)
+                np.testing.assert_allclose(b["eigs_all"][:6], e["eigs_all"][:6], rtol=1e-9)
+            np.testing.assert_array_equal(bulk.predict(X[:5000]).cpu().numpy(), eager.predict(X[:5000]).cpu().numpy())
+    finally:
+        S.BULK_FIT_BYTES = old
+    del X
+    torch.cuda.empty_cache()
+    # memory: 1 M x 1024 fp32 (4.1 GB) through the default path
+    X = synth.make_spectra_device(1_000_000, 1024, dev, seed=13)
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
+    m = SIMCA(n_components=10, model_class=0, verbose=False).fit(X, np.zeros(X.shape[0], dtype=np.int64))
+    torch.cuda.synchronize()
+    extra = torch.cuda.max_memory_allocated() - base
+    assert extra < 0.15 * X.numel() * 4, f"bulk fit allocated {extra / 2**20:.0f} MiB on top of a {X.numel() * 4 / 2**20:.0f} MiB input"
+    info = m._model[0]
+    assert info["n_samples"] == 1_000_000 and np.isfinite(info["Q_limit"])
+    ref = so.fit_one_class(X[:20000].double().cpu().numpy(), 10)
+    np.testing.assert_allclose(info["eigs_all"][:10], ref["eigs_all"][:10], rtol=0.05)      # same population, 50x more rows
+
+
+def test_subspace_eigensolver_kernels(torch):
+    """The library's own steps of the block subspace iteration (csrc/eig_sub.cu) against numpy, then the solver built from
+    them against numpy.linalg.eigh: leading eigenpairs to 1e-10, tail power sums to 1e-9 -- ragged p, batch > 1, kb < 64."""
+    rng = np.random.default_rng(29)
+    dev = torch.device("cuda")
+    lib = native.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for F, p, kb in ((3, 130, 32), (2, 1050, 32), (1, 77, 24), (1, 2048, 40)):
+        M = rng.normal(size=(F, p, 40)) * np.logspace(0, -3, 40)
+        Cn = M @ M.transpose(0, 2, 1) + 1e-6 * np.eye(p)
+        Qn = rng.normal(size=(F, p, kb))
+        Cd, Qd = torch.as_tensor(Cn, device=dev), torch.as_tensor(Qn, device=dev)
+        Z = engine._symm_mul(Cd, Qd)
+        np.testing.assert_allclose(Z.cpu().numpy(), Cn @ Qn, rtol=1e-11, atol=1e-12 * np.abs(Cn @ Qn).max())
+        H = engine._tn_small(Qd, Z)
+        np.testing.assert_allclose(H.cpu().numpy(), Qn.transpose(0, 2, 1) @ (Cn @ Qn), rtol=1e-10, atol=1e-11 * np.abs(H.cpu().numpy()).max())
+        fail = torch.zeros(F, dtype=torch.bool, device=dev)
+        Y = engine._orthonormalise(Qd, fail)
+        assert not bool(fail.any())
+        Yn = Y.cpu().numpy()
+        for f in range(F):
+            np.testing.assert_allclose(Yn[f].T @ Yn[f], np.eye(kb), atol=1e-13)
+            # same column space as the input block
+            assert np.linalg.norm(Qn[f] - Yn[f] @ (Yn[f].T @ Qn[f])) < 1e-10 * np.linalg.norm(Qn[f])
+        U = rng.normal(size=(F, kb, kb))
+        np.testing.assert_allclose(engine._mul_small(Qd, torch.as_tensor(U, device=dev)).cpu().numpy(), Qn @ U, rtol=1e-11, atol=1e-12)
+        # a rank-deficient block is reported, not silently factorised
+        Qbad = Qd.clone(); Qbad[:, :, 1] = Qbad[:, :, 0]
+        fail = torch.zeros(F, dtype=torch.bool, device=dev)
+        engine._orthonormalise(Qbad, fail)
+        assert bool(fail.all())
+        k = 12
+        w, X, tails, conv = engine.eig_topk_subspace(Cd, k, tol=1e-13, max_iter=90)
+        assert bool(conv.all())
+        for f in range(F):
+            ev, V = np.linalg.eigh(Cn[f])
+            ev, V = ev[::-1], V[:, ::-1]
+            np.testing.assert_allclose(w[f, :k].cpu().numpy(), ev[:k], rtol=1e-10)
+            Xf = X[f, :, :k].cpu().numpy()
+            np.testing.assert_allclose(np.abs(np.sum(Xf * V[:, :k], axis=0)), 1.0, atol=1e-8)
+            rest = ev[k:]
+            np.testing.assert_allclose(tails[f].cpu().numpy(), [rest.sum(), (rest ** 2).sum(), (rest ** 3).sum()], rtol=1e-9)
+
+
 def test_small_jacobi_eigensolver(torch):
     rng = np.random.default_rng(5)
     dev = torch.device("cuda")
@@ -631,6 +725,20 @@ def test_cv_grid_folds_over_ranks(torch):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["world"] == 2 and line["identical_on_all_ranks"]
+
+
+def test_fit_rows_over_ranks(torch):
+    """§8(e): the row-sharded PCA fit (partial Gram / sums / count all-reduced) equals the single-process fit on every
+    rank, through the FP64 tensor-pipe Gram and through the integer tcgen05 Gram.  Two gloo ranks on this GPU."""
+    import subprocess, sys, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OCM_DIST_BACKEND="gloo")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "dist_fit_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == 2 and line["identical_on_all_ranks"], line
 
 
 def test_bad_arguments_raise(torch):

@@ -187,3 +187,23 @@ def test_gloo_world2_moment_allreduce():
         p.join(60)
         assert p.exitcode == 0
     assert n == 301 and err < 1e-12 and ranks == [0, 1] and mx == 1.0
+
+
+def test_convvae_loads_both_reference_checkpoint_families():
+    """vae_model.py checkpoints (threshold, threshold_q, threshold_h, threshold_f) and utils/final_vaesimca.py:96
+    checkpoints (a single `q_threshold` buffer) both load with strict=True."""
+    import torch
+    from ocm_vae_simca_b200.vae import ConvVAE1D
+    mk = lambda: ConvVAE1D(64, 4, np.zeros(64, np.float32), np.ones(64, np.float32), conv_blocks=2, n_filters=4, kernel_size=5, hidden_fc=8)
+    a = mk()
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    sd["threshold_q"] = torch.tensor(3.5)
+    b = mk(); b.load_state_dict(sd, strict=True)
+    assert float(b.threshold_q) == 3.5
+    other = {k: v for k, v in sd.items() if not k.startswith("threshold")}
+    other["q_threshold"] = torch.tensor(7.25)
+    c = mk(); c.load_state_dict(other, strict=True)
+    assert float(c.threshold_q) == 7.25 and float(c.threshold_h) == 0.0
+    for k in a.state_dict():
+        if not k.startswith("threshold"):
+            assert torch.equal(c.state_dict()[k], a.state_dict()[k])
