@@ -155,6 +155,11 @@ int ocm_eig_ritz_residual_f64(const double* ZU, const double* X, const double* w
 int ocm_eig_tail_sums_f64(const double* C, const double* X, const double* w, int32_t p, int32_t kb, int32_t k,
                           int32_t batch, double* R, double* R2, double* tails, void* stream);
 
+/* ---- a4: ALL eigenvalues of a symmetric fp64 matrix (the `eigs_all` array of utils/SIMCA.py:66,:89, computed lazily):
+ * Householder tridiagonalisation + Sturm-sequence bisection (csrc/eig_full.cu).  A [p][p] is OVERWRITTEN; work holds
+ * at least 2 p + 1 doubles; d, e [p] receive the tridiagonal, w [p] the eigenvalues in DESCENDING order. */
+int ocm_eigvals_sym_f64(double* A, int32_t p, double* work, double* d, double* e, double* w, void* stream);
+
 /* ---- a5 / a9 / a10: fused scoring (replaces pca.transform + inverse_transform + the
  * two reductions of SIMCA.predict / SIMCA.transform, utils/SIMCA.py:101-145) -----------
  * For each row x:  [optional SNV] -> xc = x - mu -> t = P xc -> r = xc - P^T t ->

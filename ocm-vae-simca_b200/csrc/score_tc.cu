@@ -94,7 +94,9 @@ constexpr size_t SM_OFF_MU = SM_OFF_RING + NSTAGE * SM_STAGE;
 constexpr size_t SM_OFF_S = SM_OFF_MU + P_MAX * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
-constexpr size_t SM_TOTAL = SM_OFF_BAR + 256;
+constexpr size_t SM_OFF_MUS = SM_OFF_BAR + 256;                           // -2^XSHIFT * mu (fp16 A-operand mode)
+constexpr size_t SM_TOTAL = SM_OFF_MUS + P_MAX * 4;
+constexpr int XSHIFT = 6;                 // fp16 A operand: y = (x - mu) * 2^6, |x - mu| < 1023 stays finite in fp16
 
 // ---------------------------------------------------------------- PTX wrappers ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -265,6 +267,22 @@ __device__ __forceinline__ void split3_pack2(f32x2 x, uint32_t& w1, uint32_t& w2
     w3 = __byte_perm(s0, s1, 0x7632);
 }
 
+// 2-way fp16 split of a packed pair y (|y| < 65504): hi = rn_f16(y), lo = rn_f16(y - hi); y - (hi + lo) <= 2^-22 |y|
+// (2^-25 absolute in the subnormal range).  Six instructions per pair against nine for the 3-way bf16 split, two TMEM
+// stores per stage instead of three and two MMAs per k-step instead of three.
+__device__ __forceinline__ void split2_f16_pack2(f32x2 y, uint32_t& whi, uint32_t& wlo) {
+    uint32_t y0, y1;
+    upk2(y, y0, y1);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(whi) : "r"(y1), "r"(y0));       // high half <- y1, low half <- y0
+    uint32_t h0, h1;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+        : "=r"(h0), "=r"(h1) : "r"(whi));
+    const f32x2 r = sub2(y, pk2(h0, h1));
+    uint32_t r0, r1;
+    upk2(r, r0, r1);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(wlo) : "r"(r1), "r"(r0));
+}
+
 // exact 3-way bf16 split of two fp32 values, packed as the tensor core wants them (low half = lower K index):
 // b1 = top 16 bits, r1 = x - b1 (exact), b2 = top 16 bits of r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2
 __device__ __forceinline__ void split3_pack(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
@@ -285,8 +303,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (UMMA InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13), a_negate 13,
 // a_major 15, b_major 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major, bool a_is_f16 = false) {
+    // a format [7,10): 0 = F16, 1 = BF16 (kind::f16 takes the two operand formats independently)
+    return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | (1u << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -319,6 +338,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
 }
 
+// F16A = the A operand of the projection is a 2-term fp16 split of the prescaled centred spectrum (kind::f16 takes the
+// formats of A and B independently: A fp16 from TMEM, B = the bf16 terms of P from shared memory); false = 3 bf16 terms.
+template <bool F16A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -384,7 +406,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 2048) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
         *reinterpret_cast<uint4*>(smem + SM_OFF_P + off + 4096) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
     }
-    for (int i = tid; i < ns * STAGE_COLS; i += NTHREADS) s_mu[i] = i < a.p ? a.mu[i] : 0.f;
+    for (int i = tid; i < ns * STAGE_COLS; i += NTHREADS) {
+        const float m = i < a.p ? a.mu[i] : 0.f;
+        s_mu[i] = m;
+        if (F16A) reinterpret_cast<float*>(smem + SM_OFF_MUS)[i] = -m * (float)(1 << XSHIFT);
+    }
     for (int i = tid; i < NCOMP * NCOMP; i += NTHREADS) {
         const int r = i / NCOMP, c = i % NCOMP;
         s_S[i] = (r < a.A && c < a.A) ? a.Sinv[r * a.A + c] : 0.f;
@@ -450,6 +476,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
         };
 
+        // same, for the fp16 A operand: y = x * 2^XSHIFT - mu * 2^XSHIFT in one packed FMA (exact scaling)
+        auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) {
+            mbar_wait(bar_full, ring_phase, wctx);
+            const uint32_t kx = __float_as_uint((float)(1 << XSHIFT));
+            const f32x2 k2 = pk2(kx, kx);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const ulonglong2 v = lds128(st + xo[i]);
+                const ulonglong2 m = lds128(mu_addr + (uint32_t)(SM_OFF_MUS - SM_OFF_MU) + 16u * (uint32_t)i);
+                y[2 * i] = fma2(v.x, k2, m.x);
+                y[2 * i + 1] = fma2(v.y, k2, m.y);
+            }
+            mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
+            st += (uint32_t)SM_STAGE; bar_full += 8u;
+            if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
+        };
+
         for (int64_t k = 0; k < my_tiles; ++k) {
             if (named_bar_or(2, NCONV, aborted())) {
                 // the CTA's protocol is dead: every row it still owns is marked, nothing else is touched
@@ -471,19 +514,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     f32x2 xc[QCOLS / 2];
-                    load_stage(mu_addr, xc);
+                    if (F16A) load_stage_scaled(mu_addr, xc); else load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
                     mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx);                  // MMAs of the buffer's previous user retired
                     tc_fence_after();
-                    uint32_t w1[8], w2[8], w3[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        split3_pack2(xc[i], w1[i], w2[i], w3[i]);
-                    }
                     const uint32_t abase = abase0 + (uint32_t)(b * 96);
-                    tc_st8(abase, w1);
-                    tc_st8(abase + 32, w2);
-                    tc_st8(abase + 64, w3);
+                    if (F16A) {
+                        uint32_t w1[8], w2[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split2_f16_pack2(xc[i], w1[i], w2[i]);
+                        tc_st8(abase, w1);
+                        tc_st8(abase + 32, w2);
+                    } else {
+                        uint32_t w1[8], w2[8], w3[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            split3_pack2(xc[i], w1[i], w2[i], w3[i]);
+                        }
+                        tc_st8(abase, w1);
+                        tc_st8(abase + 32, w2);
+                        tc_st8(abase + 64, w3);
+                    }
                     tc_wait_st();
                     tc_fence_before();
                     mbar_arrive(BAR(B_AFULL + b));
@@ -513,7 +564,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     for (int ks = 0; ks < NACC_MAIN; ++ks) add_pair(TM_D1 + 48u * ks + 16u, TM_D1 + 48u * ks + 32u);   // (1,2) (1,3)
                     add_pair(TM_D2 + 0u, TM_D2 + 16u);            // (2,1) (2,2) of MMA warp 0
                     add_pair(TM_D2 + 32u, TM_D2 + 48u);           //                 MMA warp 1
-                    add_pair(TM_D3 + 0u, TM_D3 + 16u);            // (3,1) of both MMA warps
+                    if (!F16A) add_pair(TM_D3 + 0u, TM_D3 + 16u);   // (3,1) of both MMA warps (3-term A operand only)
                     uint32_t m0[16], m1[16];
                     tc_ld16(lane_addr + TM_D1 + 0u, m0);
                     tc_ld16(lane_addr + TM_D1 + 48u, m1);
@@ -525,6 +576,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     tc_wait_ld16x2(m0, m1);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
+                    if (F16A) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) t[i] *= 1.0f / (float)(1 << XSHIFT);      // undo the prescale (exact)
+                    }
                 }
                 float t2 = 0.f;
                 if (s_diag) {
@@ -641,9 +696,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         // buffer's barriers is waited on by ONE warp in order (a parity wait issued a phase early returns at once).
         // =====================================================================================
         const int mw = warp - W_MMA;                                        // 0 or 1
-        constexpr uint32_t IDESC_N48 = make_idesc(TILE_M, 48, false, false);
-        constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false);
-        constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false);
+        constexpr uint32_t IDESC_N48 = make_idesc(TILE_M, 48, false, false, F16A);
+        constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false, F16A);
+        constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false, F16A);
         constexpr uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, false, true);        // B = P read MN-major
         constexpr uint32_t lbo2 = (uint32_t)SM_PATOM, sbo2 = 1024u;
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
@@ -672,7 +727,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                         const uint32_t a0 = tmem + TM_ABUF + (uint32_t)(b * 96 + 8 * ks);
                         tc_mma_ts(tmem + TM_D1 + 48u * (uint32_t)ks, a0, d_b, IDESC_N48, first);
                         tc_mma_ts(tmem + TM_D2 + 32u * (uint32_t)mw, a0 + 32, d_b, IDESC_N32, (first | (uint32_t)kk) != 0 ? 1u : 0u);
-                        tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (first | (uint32_t)kk) != 0 ? 1u : 0u);
+                        if (!F16A) tc_mma_ts(tmem + TM_D3 + 16u * (uint32_t)mw, a0 + 64, d_b, IDESC_N16, (first | (uint32_t)kk) != 0 ? 1u : 0u);
                     }
                     tc_commit_elect(BAR(B_AFREE + b));
                 }
@@ -778,7 +833,9 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
                tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0};
-    auto kern = tc::score_tc_kernel;
+    // OCM_SCORE_BF16A=1 keeps the 3-term bf16 A operand of round 1 (A/B runs); default: 2-term fp16 A operand
+    static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();
+    auto kern = bf16a ? tc::score_tc_kernel<false> : tc::score_tc_kernel<true>;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
     int64_t blocks = sm_count();

@@ -1,7 +1,9 @@
 """Device pipeline of the SIMCA hot path: thin Python over the C ABI (include/ocm_simca.h).
 
-torch is used for device memory, streams and (multi-GPU) torch.distributed only; every
-numerical step is a call into libocm_simca_b200.so.  Nothing here falls back to the CPU.
+torch is used for device memory, streams, the random start block of the subspace iteration and (multi-GPU)
+torch.distributed; the numerical steps are calls into libocm_simca_b200.so.  One library call is left on a fallback
+path: `eigh_topk` (torch.linalg.eigh, cuSOLVER) for a covariance whose subspace iteration does not converge (flat
+spectrum at n_components) or a fit that asks for `full_spectrum=True` WITH vectors.  Nothing here falls back to the CPU.
 
     moments -> covariance -> eigh -> (mean, loadings, eigenvalues)      fit   (SIMCA.py:62-75)
     fused score kernel -> T2, Q, accept                                 predict (SIMCA.py:120-154)
@@ -488,10 +490,23 @@ def fit_pca_folds(X, row_sets, k) -> list:
     return models
 
 
+def eigvals_sym(Cm):
+    """All eigenvalues (descending, fp64 device tensor) of a symmetric matrix by the library's own Householder
+    tridiagonalisation + Sturm bisection (ocm_eigvals_sym_f64, csrc/eig_full.cu)."""
+    torch = _torch()
+    p = Cm.shape[0]
+    A = Cm.contiguous().clone()                       # overwritten by the reduction
+    work = torch.empty(2 * p + 8, dtype=torch.float64, device=Cm.device)
+    d = torch.empty(p, dtype=torch.float64, device=Cm.device)
+    e = torch.empty(p, dtype=torch.float64, device=Cm.device)
+    w = torch.empty(p, dtype=torch.float64, device=Cm.device)
+    native.check(native.lib().ocm_eigvals_sym_f64(_p(A), p, _p(work), _p(d), _p(e), _p(w), _stream()), "ocm_eigvals_sym_f64")
+    return w
+
+
 def _full_spectrum(Cm, n, p):
     """All eigenvalues of the covariance, descending, as the reference keeps them (min(n, p) entries)."""
-    torch = _torch()
-    evals = torch.flip(torch.linalg.eigvalsh(Cm), dims=[-1])
+    evals = eigvals_sym(Cm)
     m = min(n, p)
     eigs = evals[:m].clamp_min(0.0).cpu().numpy()
     if n <= p:

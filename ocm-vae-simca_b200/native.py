@@ -109,6 +109,7 @@ SIGNATURES = {
     "ocm_eig_mul_small_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ocm_eig_ritz_residual_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ocm_eig_tail_sums_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "ocm_eigvals_sym_f64": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ocm_eigh_small_f64": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "ocm_simca_score_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                       _vp, _vp, _vp, _vp, _vp]),

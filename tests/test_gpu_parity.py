@@ -402,6 +402,28 @@ def test_subspace_eigensolver_kernels(torch):
             np.testing.assert_allclose(tails[f].cpu().numpy(), [rest.sum(), (rest ** 2).sum(), (rest ** 3).sum()], rtol=1e-9)
 
 
+def test_full_spectrum_solver(torch):
+    """ocm_eigvals_sym_f64 (Householder tridiagonalisation + bisection) against numpy.linalg.eigvalsh: covariance-like
+    matrices with a 1e-8 dynamic range, a rank-deficient one, tiny and odd sizes; absolute error a few ulp of |A|."""
+    rng = np.random.default_rng(31)
+    dev = torch.device("cuda")
+    for p in (1, 2, 3, 17, 130, 700, 1050):
+        M = rng.normal(size=(p, max(p // 2, 1))) * np.logspace(0, -4, max(p // 2, 1))
+        A = M @ M.T                                        # rank p/2: half of the spectrum is (numerically) zero
+        if p > 3:
+            A += 1e-9 * np.diag(rng.uniform(size=p))
+        ref = np.linalg.eigvalsh(A)[::-1]
+        w = engine.eigvals_sym(torch.as_tensor(A, device=dev)).cpu().numpy()
+        assert np.all(np.diff(w) <= 0)
+        np.testing.assert_allclose(w, ref, rtol=0, atol=4e-14 * max(abs(ref[0]), 1e-300) * max(p, 8) ** 0.5)
+    X, y = synth.make_class_dataset(200, 100, 700, seed=0)
+    m = SIMCA(n_components=5, model_class=0, verbose=False).fit(X, y)
+    full = np.asarray(m._model[0]["eigs_all"])           # the lazy entry goes through the solver
+    assert full.shape == (200,)
+    ref = so.fit_one_class(X[y == 0], 5)["eigs_all"]
+    np.testing.assert_allclose(full[:150], ref[:150], rtol=1e-8)
+
+
 def test_small_jacobi_eigensolver(torch):
     rng = np.random.default_rng(5)
     dev = torch.device("cuda")

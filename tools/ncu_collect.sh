@@ -1,0 +1,20 @@
+#!/bin/bash
+# One ncu --set full capture per hot kernel (run under gpurun, 1 GPU); reports land in gpurun_out/.
+# usage: tools/ncu_collect.sh <tag>
+tag=${1:-r02}
+set -x
+python tools/kernels_once.py all > gpurun_out/${tag}_kernels_plain.log 2>&1 || exit 1
+cap() {  # name, regex, script arg
+  ncu --set full --clock-control none --import-source on -k regex:"$2" -c 1 -s "${4:-1}" -o gpurun_out/${tag}_$1 -f \
+      python tools/kernels_once.py $3 > gpurun_out/${tag}_$1.log 2>&1
+}
+cap score_tc "score_tc_kernel" score 2
+cap gram_tc "gram_tc_kernel" gram 2
+cap gram_quantize "gram_quantize_kernel" gram 1
+cap colstats_minmax "colstats_minmax_kernel" gram 0
+cap score_multiA "score_simt_kernel" all 1
+cap preprocess "preprocess_kernel" all 1
+cap savgol "savgol_kernel" all 1
+cap latent "latent_score_kernel" all 1
+cap jacobi "jacobi_eigh_kernel" all 0
+cap symm_mul "symm_mul_kernel" score 3
