@@ -447,7 +447,7 @@ def vae_leg(args, device, group, rank, world, local_rank):
     model = vae
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(vae, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(vae.parameters(), lr=1e-3, fused=True)
+    opt = torch.optim.Adam(vae.parameters(), lr=1e-4, fused=True)
     Bt = 4096
 
     def train_step(i):
@@ -473,13 +473,14 @@ def vae_leg(args, device, group, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize()
     train_ms = odist.max_over_ranks(e0.elapsed_time(e1), device) / tsteps
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # calibration statistics of the latent means (VAE_SIMCA.py:245-248), all-reduced over the shards
     vae.eval()
     Bs = 8192
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.no_grad():                                     # calibration statistics in fp32
         mu_cal = torch.cat([vae.encode((X[r:r + Bs] - vae.spec_mean) / vae.spec_std)[0].float() for r in range(0, min(n, 65536), Bs)])
+    mu_cal = torch.nan_to_num(mu_cal)
     cnt = torch.tensor([float(mu_cal.shape[0])], dtype=torch.float64, device=device)
     s1 = mu_cal.double().sum(0); s2 = mu_cal.double().T @ mu_cal.double()
     if group is not None:
@@ -487,7 +488,7 @@ def vae_leg(args, device, group, rank, world, local_rank):
             dist.all_reduce(t, group=group)
     m = s1 / cnt
     cov = (s2 - cnt * torch.outer(m, m)) / (cnt - 1) + 1e-6 * torch.eye(d, dtype=torch.float64, device=device)
-    vae.latent_mean.copy_(m.float()); vae.latent_cov_inv.copy_(torch.linalg.inv(cov).float())
+    vae.latent_mean.copy_(m.float()); vae.latent_cov_inv.copy_(torch.linalg.pinv(cov, hermitian=True).float())
 
     d2_all = torch.empty(n, device=device); q_all = torch.empty(n, device=device)
 
@@ -572,7 +573,9 @@ def main():
     if args.force_simt:
         kernel_name = "score_simt_kernel"
     elif lib.ocm_simca_score_tc_supported(rows, p, p, A, 0, C_void(X)):
-        kernel_name = "score_tc_kernel<false> (tcgen05.mma kind::f16 bf16x3, TMEM operands, TMA ring)"
+        bf16a = os.environ.get("OCM_SCORE_BF16A", "0") == "1"
+        kernel_name = ("score_tc_kernel<false> (tcgen05.mma kind::f16, 3-term bf16 operands, TMEM A operand, TMA ring)" if bf16a else
+                       "score_tc_kernel<true> (tcgen05.mma kind::f16, 2-term fp16 A operand from TMEM, 3-term fp16 loadings, TMA ring)")
     elif lib.ocm_simca_score_rowteam_supported(rows, p, p, A, 0, C_void(X)):
         kernel_name = f"score_rowteam_kernel<{A},{p // 128 if p <= 1024 else 8},{128 if p <= 1024 else 256}> (FFMA2)"
     else:

@@ -115,7 +115,8 @@ int ocm_gram_tc_f64(const double* X, int64_t ldx, const int64_t* row_idx, int64_
                     const double* shift, const float* colmin, const float* colmax, int32_t products,
                     void* work, int64_t work_bytes, double* G, double* colsum, int64_t* flags, void* stream);
 
-/* Combine per-partition moments into a covariance:  with weights w[g] in {0,1,...}
+/* Combine per-partition moments into a covariance:  with weights w[g] (0 / 1 to select partitions, -1 to DOWNDATE a
+ * held-out part from a pool: CV folds)
  *   N = sum w_g n_g,  s = sum w_g colsum_g,  G = sum w_g G_g,  d = s/N,
  *   mean = shift + d,  C = (G - N d d^T)/(N-1)  (full symmetric p x p written to C);
  *   delta[p] (required scratch/output) receives d, mean[p] may be NULL.

@@ -39,19 +39,24 @@ using namespace ptx;
 
 constexpr int S = 4;                        // int8 digit planes
 constexpr int TILE = 128;                   // row block of the output tile = MMA M; column blocks are TILE wide too
-constexpr int KB = 32;                      // rows per pipeline stage = K of one int8 MMA
-constexpr int BOX_BYTES = TILE * KB;        // 4096: one plane's box, 32 rows of 128 B, SWIZZLE_128B
+constexpr int KSTEP = 32;                   // K of one int8 MMA
 constexpr int NTHREADS = 192;               // warp 0: TMA, warp 1: MMA issue + TMEM owner, warps 2..5: flush
 constexpr int MAX_CHAIN_ROWS = 32704;       // 4 products x 128 x 128 x rows < 2^31
 constexpr int V_LIMIT = 0x5FFFFFFF;         // clamp of the fixed-point value (top digit stays <= 96)
-constexpr int QROWS = 64;                   // the quantiser pads a chunk to a multiple of this many rows
+constexpr int QROWS = 64;
+#ifndef OCM_GRAM_DEFAULT_MODE
+#define OCM_GRAM_DEFAULT_MODE 1
+#endif
+//                   // the quantiser pads a chunk to a multiple of this many rows
 // NB = column blocks per CTA tile.  NB = 1: 128 x 128 tiles, four accumulators (one pass over the data for the ten
 // leading products).  NB = 2: 128 x 256 tiles, MMA N = 256, two accumulators, two weights per pass -- at N = 128 the
 // operand reads of the MMAs (8 KB per 64 cycles = 128 B/clk) plus the TMA writes of the next stage exceed the
 // 128 B/clk of the shared-memory pipe (measured: 62 % of the MMA rate); at N = 256 an MMA reads 12 KB per 128 cycles.
 template <int NB> struct Cfg {
+    static constexpr int KB = NB == 1 ? 64 : 32;                          // rows per pipeline stage (KB / 32 MMAs per product)
+    static constexpr int BOX_BYTES = TILE * KB;                           // one plane's box: KB rows of 128 B, SWIZZLE_128B
     static constexpr int STAGE_BYTES = (S + S * NB) * BOX_BYTES;          // A planes + B planes x column blocks
-    static constexpr int NSTAGE = NB == 1 ? 6 : 4;
+    static constexpr int NSTAGE = NB == 1 ? 3 : 4;
     static constexpr size_t SM_OFF_BAR = (size_t)NSTAGE * STAGE_BYTES;
     static constexpr size_t SM_TOTAL = SM_OFF_BAR + 128 + 1024;           // + barriers + slack for the 1024-byte alignment
     static constexpr int MAX_ACC = 4 / NB;
@@ -69,7 +74,7 @@ struct Args {
     int p;                  // columns of G
     int nt;                 // 128-column blocks per edge
     int ntiles;             // CTA tiles (upper triangle)
-    int nstages;            // stages in this chunk (rows_pad / KB)
+    int nstages;            // stages in this chunk (ceil(rows / KB))
     int stages_per_split;
     const double* inv_scale;    // [p_pad] 2^-sc
     double* part;           // [splits][ntiles][8 NB][128][16] fp64 partial tiles, each owned by ONE CTA of a launch
@@ -251,7 +256,7 @@ template <int NB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Args a) {
     using C = Cfg<NB>;
-    constexpr int NSTAGE = C::NSTAGE;
+    constexpr int NSTAGE = C::NSTAGE, KB = C::KB, BOX_BYTES = C::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms are 1024-byte aligned
     const uint32_t bar0 = sb + (uint32_t)C::SM_OFF_BAR;
@@ -316,27 +321,32 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         uint32_t used = 0;
         int slot = 0;
         uint32_t ph = 0;
+        bool fine = true;
         for (int s = 0; s < nst; ++s) {
-            if (!mbar_wait_bounded(BAR_FULL(slot), ph, wctx, 12u)) break;
+            if (!__all_sync(0xffffffffu, mbar_wait_bounded(BAR_FULL(slot), ph, wctx, 12u))) { fine = false; break; }
             tc_fence_after();
             const uint32_t base = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
             // MN-major SW128 operands: 128 columns = one 128-byte atom row, 8-row groups 1024 B apart (SBO), one K = 32
             // MMA covers the four groups of a box; the B operand of an N = 256 MMA is two atoms BOX_BYTES apart (LBO)
-            for (int m = 0; m < a.pr.n; ++m) {
-                const uint32_t acc = a.pr.acc[m];
-                const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * BOX_BYTES, BOX_BYTES, 1024);
-                const uint64_t db = make_desc_sw128(base + b_off + (uint32_t)a.pr.l[m] * (uint32_t)(NB * BOX_BYTES), BOX_BYTES, 1024);
-                tc_mma_ss_i8(tmem + acc * (uint32_t)(TILE * NB), da, db, IDESC, (used >> acc) & 1u);
-                used |= 1u << acc;
+#pragma unroll
+            for (int ks = 0; ks < KB / KSTEP; ++ks) {              // the next k-step starts 32 rows = 4096 B further
+                for (int m = 0; m < a.pr.n; ++m) {
+                    const uint32_t acc = a.pr.acc[m];
+                    const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * BOX_BYTES + (uint32_t)ks * 4096u, BOX_BYTES, 1024);
+                    const uint64_t db = make_desc_sw128(base + b_off + (uint32_t)a.pr.l[m] * (uint32_t)(NB * BOX_BYTES) + (uint32_t)ks * 4096u,
+                                                        BOX_BYTES, 1024);
+                    tc_mma_ss_i8(tmem + acc * (uint32_t)(TILE * NB), da, db, IDESC, (used >> acc) & 1u);
+                    used |= 1u << acc;
+                }
             }
             tc_commit_elect(BAR_EMPTY(slot));                   // the slot is free once these MMAs have read it
             if (++slot == NSTAGE) { slot = 0; ph ^= 1u; }
         }
-        tc_commit_elect(bar_acc);
+        if (fine) tc_commit_elect(bar_acc);         // an abandoned pipeline publishes nothing: the flush marks the tile NaN
     } else {
         // ===== flush: int32 accumulators -> int64 -> fp64 -> += into this CTA's own partial tile ====================
         const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
-        const bool ok = mbar_wait_bounded(bar_acc, 0, wctx, 13u);      // false: the pipeline gave up -> the tile becomes NaN
+        const bool ok = __all_sync(0xffffffffu, mbar_wait_bounded(bar_acc, 0, wctx, 13u));      // false: the pipeline gave up -> the tile becomes NaN
         tc_fence_after();
         const int r = 32 * q + lane;                             // row of the tile
         const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * a.pr.dmin);
@@ -377,16 +387,203 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem, 512u);
 }
 
-static int make_planes_map(CUtensorMap* map, const uint8_t* planes, int p_pad, int rows_cap) {
+// ------------------------------------------------------------------------------------------ multiply, CTA pair
+// cta_group::2: the two CTAs of a cluster share one MMA of M = 256 x N = 128.  Each CTA owns 128 rows of the pair tile
+// (its own A planes, its own 4 x 128 accumulator columns) and holds only HALF of the B planes (64 columns, SWIZZLE_64B
+// boxes), so per MMA it reads 4 KB of A + 2 KB of B from shared memory instead of 8 KB, and the TMA writes 48 KB per
+// stage instead of 64 KB: the shared-memory pipe (128 B/clk) no longer caps the MMA rate of the 128 x 128 single-CTA
+// kernel (~65 % measured).  Leader = cluster rank 0: it alone issues the MMAs; both CTAs' TMA loads signal ITS full
+// barrier; its commits free the slot in both CTAs (multicast) and publish the accumulators to both.
+struct Cfg2 {
+    static constexpr int KB = 64;
+    static constexpr int A_BOX = TILE * KB;                  // 8192: 128 columns x 64 rows, SWIZZLE_128B
+    static constexpr int B_BOX = (TILE / 2) * KB;            // 4096:  64 columns x 64 rows, SWIZZLE_64B
+    static constexpr int STAGE_BYTES = S * (A_BOX + B_BOX);  // 49152
+    static constexpr int NSTAGE = 4;
+    static constexpr size_t SM_OFF_BAR = (size_t)NSTAGE * STAGE_BYTES;
+    static constexpr size_t SM_TOTAL = SM_OFF_BAR + 128 + 1024;
+};
+
+// pair tile -> (row pair-block tp: row blocks 2 tp, 2 tp + 1; column block tj >= 2 tp)
+__host__ __device__ inline void pair_coords(int tile, int nt, int& tp, int& tj) {
+    int t = tile; tp = 0;
+    while (t >= nt - 2 * tp) { t -= nt - 2 * tp; ++tp; }
+    tj = 2 * tp + t;
+}
+inline int pair_count(int nt) {
+    int c = 0;
+    for (int tp = 0; 2 * tp < nt; ++tp) c += nt - 2 * tp;
+    return c;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ Args a) {
+    using C = Cfg2;
+    constexpr int NSTAGE = C::NSTAGE, KB = C::KB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = sb + (uint32_t)C::SM_OFF_BAR;
+    auto BAR_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(NSTAGE + s); };
+    const uint32_t bar_acc = bar0 + 8u * (uint32_t)(2 * NSTAGE);
+    const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * NSTAGE + 1);
+    const WaitCtx wctx{tmem_slot + 4u, a.status, 1u << 22};
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int unit = blockIdx.x >> 1;
+    const int tile = unit % a.ntiles, split = unit / a.ntiles;
+    int tp, tj;
+    pair_coords(tile, a.nt, tp, tj);
+    const int ti = 2 * tp + rank;                                // this CTA's row block
+    const int st0 = split * a.stages_per_split;
+    const int nst = min(a.nstages, st0 + a.stages_per_split) - st0;
+    if (nst <= 0) return;                                        // uniform over the pair
+
+    if (tid == 0) {
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(wctx.abort_addr), "r"(0u) : "memory");
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+        mbar_init(bar_acc, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapB); }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ===== TMA producer (each CTA loads its own A planes and its half of the B planes) =====================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_last();
+            const int nl = a.pr.nload - a.pr.kmin;
+            const uint32_t bytes_pair = (uint32_t)(2 * nl * (C::A_BOX + C::B_BOX));
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int s = 0; s < nst; ++s) {
+                if (!mbar_wait_bounded(BAR_EMPTY(slot), ph ^ 1u, wctx, 21u)) break;
+                if (rank == 0) mbar_expect_tx(BAR_FULL(slot), bytes_pair);
+                const uint32_t dst = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
+                const int row = (st0 + s) * KB;
+                for (int k = a.pr.kmin; k < a.pr.nload; ++k) {
+                    tma_load_3d_2sm(dst + (uint32_t)(k * C::A_BOX), &tmapA, ti * TILE, row, k, BAR_FULL(slot), pol);
+                    tma_load_3d_2sm(dst + (uint32_t)(S * C::A_BOX + k * C::B_BOX), &tmapB, tj * TILE + (TILE / 2) * rank, row, k,
+                                    BAR_FULL(slot), pol);
+                }
+                if (++slot == NSTAGE) { slot = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issue: the leader only ==========================================================================
+        if (rank == 0) {
+            constexpr uint32_t IDESC = make_idesc_i8(2 * TILE, TILE, true, true);
+            uint32_t used = 0;
+            int slot = 0;
+            uint32_t ph = 0;
+            bool fine = true;
+            for (int s = 0; s < nst; ++s) {
+                if (!__all_sync(0xffffffffu, mbar_wait_bounded(BAR_FULL(slot), ph, wctx, 22u))) { fine = false; break; }
+                tc_fence_after();
+                const uint32_t base = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < KB / KSTEP; ++ks) {
+                    for (int m = 0; m < a.pr.n; ++m) {
+                        const uint32_t acc = a.pr.acc[m];
+                        // A: MN-major SW128 (128 rows of G = 128 bytes), 8-row K groups 1024 B apart, k-step = 4096 B
+                        const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * C::A_BOX + (uint32_t)ks * 4096u, C::A_BOX, 1024);
+                        // B: this CTA's 64 columns, MN-major SW64 (64-byte rows), 8-row K groups 512 B apart, k-step = 2048 B
+                        const uint64_t db = make_desc_sw64(base + (uint32_t)(S * C::A_BOX) + (uint32_t)a.pr.l[m] * C::B_BOX + (uint32_t)ks * 2048u,
+                                                           C::B_BOX, 512);
+                        tc_mma_ss_i8_2sm(tmem + acc * (uint32_t)TILE, da, db, IDESC, (used >> acc) & 1u);
+                        used |= 1u << acc;
+                    }
+                }
+                tc_commit_2sm_elect(BAR_EMPTY(slot));           // frees the slot in BOTH CTAs
+                if (++slot == NSTAGE) { slot = 0; ph ^= 1u; }
+            }
+            if (fine) tc_commit_2sm_elect(bar_acc);             // accumulators complete: both CTAs flush their half
+        }
+        __syncwarp();
+    } else {
+        // ===== flush: this CTA's 128 rows of the pair tile =========================================================
+        const int q = warp & 3;
+        const bool ok = __all_sync(0xffffffffu, mbar_wait_bounded(bar_acc, 0, wctx, 23u));
+        tc_fence_after();
+        const int r = 32 * q + lane;
+        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * a.pr.dmin);
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+        double* tile_base = a.part + (((int64_t)split * a.ntiles + tile) * 2 + rank) * (int64_t)(TILE * TILE);
+        for (int c16 = 0; c16 < TILE / 16; ++c16) {
+            long long tsum[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) tsum[e] = 0;
+            for (int ac = 0; ac < a.pr.nacc; ++ac) {
+                uint32_t v[16];
+                tc_ld16(lane_addr + (uint32_t)(ac * TILE + 16 * c16), v);
+                tc_wait_ld();
+                tc_pin16(v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) tsum[e] += (long long)(int)v[e] << (8 * ac);
+            }
+            const double* isc = a.inv_scale + tj * TILE + 16 * c16;
+            double2* dst = reinterpret_cast<double2*>(tile_base + ((int64_t)c16 * TILE + r) * 16);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                double2 cur = dst[e];
+                cur.x += (double)tsum[2 * e] * (w_i * isc[2 * e]);
+                cur.y += (double)tsum[2 * e + 1] * (w_i * isc[2 * e + 1]);
+                if (!ok) cur.x = cur.y = __longlong_as_double(0x7ff8000000000000ll);
+                dst[e] = cur;
+            }
+        }
+        tc_fence_before();
+    }
+    if (lds32_volatile(wctx.abort_addr)) {
+        for (int i = 0; i < 100; ++i) __nanosleep(2000);
+    }
+    __syncthreads();
+    cluster_sync_all();                                          // nobody leaves while the peer may still read its shared memory
+    if (warp == 1) tmem_dealloc_2sm(tmem, 512u);
+}
+
+// fold for the pair layout: partial tile (pair tile, rank) covers row block 2 tp + rank, column block tj
+__global__ void __launch_bounds__(256)
+gram_fold2_kernel(const double* __restrict__ part, int splits, int nt, int ntiles, int p, const double* __restrict__ colsumsq_q,
+                  const double* __restrict__ inv_scale, double* __restrict__ G) {
+    const int tile = blockIdx.x >> 1, rank = blockIdx.x & 1;
+    int tp, tj;
+    pair_coords(tile, nt, tp, tj);
+    const int ti = 2 * tp + rank;
+    for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+        const int r = idx >> 7, c = idx & 127;
+        const int i = ti * TILE + r, j = tj * TILE + c;
+        if (i >= p || j >= p || j < i) continue;
+        double acc;
+        if (i == j) {
+            acc = colsumsq_q[i] * inv_scale[i] * inv_scale[i];
+        } else {
+            acc = 0.0;
+            const int64_t off = ((int64_t)(c >> 4) * TILE + r) * 16 + (c & 15);
+            for (int sp = 0; sp < splits; ++sp) acc += part[(((int64_t)sp * ntiles + tile) * 2 + rank) * (int64_t)(TILE * TILE) + off];
+        }
+        G[(int64_t)i * p + j] += acc;
+    }
+}
+
+static int make_planes_map(CUtensorMap* map, const uint8_t* planes, int p_pad, int rows_cap, int KB, int box_cols = TILE) {
     EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return (int)cudaErrorNotSupported; }
     const cuuint64_t dims[3] = {(cuuint64_t)p_pad, (cuuint64_t)rows_cap, (cuuint64_t)S};
     const cuuint64_t strides[2] = {(cuuint64_t)p_pad, (cuuint64_t)p_pad * (cuuint64_t)rows_cap};
-    const cuuint32_t box[3] = {(cuuint32_t)TILE, (cuuint32_t)KB, 1};      // 128 columns x 32 rows of one plane
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)KB, 1};  // box_cols columns x KB rows of one plane
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(planes), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == TILE ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return (int)cudaErrorInvalidValue; }
     return 0;
 }
@@ -423,14 +620,22 @@ static int choose_splits(int ntiles, int nstages, int sms, int nprod, int nb) {
     double best = 1e300;
     for (int sp = 1; sp <= max_splits; ++sp) {
         const int64_t waves = ((int64_t)ntiles * sp + sms - 1) / sms;
-        const double cost = (double)waves * ((double)((nstages + sp - 1) / sp) * 64.0 * nb * nprod + 15000.0);
+        const double cost = (double)waves * ((double)((nstages + sp - 1) / sp) * 64.0 * nb * nprod * (nb == 1 ? 2 : 1) + 15000.0);
         if (cost < best * 0.999) { best = cost; best_sp = sp; }
     }
     return best_sp;
 }
 
-static int column_blocks() {       // OCM_GRAM_NB=1 selects the 128 x 128 tile kernel (A/B runs); default 128 x 256
-    static const int nb = [] { const char* e = getenv("OCM_GRAM_NB"); return (e && e[0] == '1') ? 1 : 2; }();
+// kernel variant: 1 = 128 x 128 tile per CTA, 2 = 128 x 256 tile per CTA, 3 = 256 x 128 tile per CTA PAIR (cta_group::2).
+// OCM_GRAM_NB picks one for A/B runs.
+static int column_blocks() {
+    static const int nb = [] {
+        const char* e = getenv("OCM_GRAM_NB");
+        if (e && e[0] == '2') return 2;
+        if (e && e[0] == '3') return 3;
+        if (e && e[0] == '1') return 1;
+        return OCM_GRAM_DEFAULT_MODE;
+    }();
     return nb;
 }
 
@@ -443,13 +648,14 @@ static Layout workspace_layout(int64_t n, int p) {
     L.nb = column_blocks();
     L.p_pad = (p + TILE - 1) / TILE * TILE;
     L.nt = L.p_pad / TILE;
-    L.ntiles = L.nb == 1 ? tile_count<1>(L.nt) : tile_count<2>(L.nt);
+    L.ntiles = L.nb == 1 ? tile_count<1>(L.nt) : L.nb == 2 ? tile_count<2>(L.nt) : pair_count(L.nt);   // mode 3: PAIR tiles
     int64_t rc = (n + QROWS - 1) / QROWS * QROWS;
     if (rc > MAX_CHAIN_ROWS) rc = MAX_CHAIN_ROWS;
     if (rc < QROWS) rc = QROWS;
     L.rows_cap = (int)rc;
     const int sms = sm_count();
-    L.max_splits = L.ntiles >= sms ? 1 : sms / L.ntiles;
+    const int ctas_per_tile = L.nb == 3 ? 2 : 1;
+    L.max_splits = L.ntiles * ctas_per_tile >= sms ? 1 : sms / (L.ntiles * ctas_per_tile);
     size_t o = 0;
     L.off_scale = o; o += sizeof(double) * L.p_pad;
     L.off_inv = o; o += sizeof(double) * (L.p_pad + TILE);      // + one block: the padded second column block of an odd edge
@@ -457,7 +663,7 @@ static Layout workspace_layout(int64_t n, int p) {
     L.off_colsumsq = o; o += sizeof(double) * L.p_pad;
     L.off_flags = o; o += 64;
     o = (o + 1023) / 1024 * 1024;
-    L.off_part = o; o += sizeof(double) * (size_t)L.max_splits * L.ntiles * TILE * TILE * L.nb;
+    L.off_part = o; o += sizeof(double) * (size_t)L.max_splits * L.ntiles * TILE * TILE * 2;      // 2: column blocks (mode 2) or CTAs (mode 3)
     o = (o + 1023) / 1024 * 1024;
     L.plane_buf_bytes = (size_t)S * L.rows_cap * L.p_pad;
     const int nbuf = n > L.rows_cap ? 2 : 1;                 // double-buffered when there is more than one chunk
@@ -525,7 +731,7 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
     // passes: which weights 256^d go into which launch (one accumulator per weight, 4 / NB accumulators per launch)
     Products passes[4];
     int npass = 0;
-    if (L.nb == 1) {
+    if (L.nb != 2) {
         passes[npass++] = product_table(3, 6);
         if (products == 13) passes[npass++] = product_table(2, 2);
         if (products == 16) passes[npass++] = product_table(0, 2);
@@ -537,22 +743,29 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
     }
 
     // the K split is fixed for the call (the partial buffer is indexed by it); the last, shorter chunk just has fewer stages
+    const int KB = L.nb == 2 ? Cfg<2>::KB : 64;
+    const int ctas_per_tile = L.nb == 3 ? 2 : 1;
     const int nstages_full = (int)(((n < L.rows_cap ? n : L.rows_cap) + KB - 1) / KB);
-    int splits = choose_splits(L.ntiles, nstages_full, sms, passes[0].n, L.nb);
+    int splits = choose_splits(L.ntiles * ctas_per_tile, nstages_full, sms, passes[0].n, L.nb == 2 ? 2 : 1);
     if (splits > L.max_splits) splits = L.max_splits;
 
     OCM_CUDA(cudaMemsetAsync(wflags, 0, 64, stream));
-    OCM_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)splits * L.ntiles * TILE * TILE * L.nb, stream));
+    OCM_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)splits * L.ntiles * TILE * TILE * 2, stream));
     OCM_CUDA(cudaMemsetAsync(inv_scale + L.p_pad, 0, sizeof(double) * TILE, stream));
     gram_scale_kernel<<<(L.p_pad + 255) / 256, 256, 0, stream>>>(colmin, colmax, shift, p, L.p_pad, scale, inv_scale, colsum_q, colsumsq_q);
     int rc = check_launch("gram_scale_kernel");
     if (rc) return rc;
 
-    CUtensorMap tmap[2];
+    CUtensorMap tmap[2], tmapB[2];
     for (int b = 0; b < (nchunks > 1 ? 2 : 1); ++b) {
-        rc = make_planes_map(&tmap[b], wb + L.off_planes + (size_t)b * L.plane_buf_bytes, L.p_pad, L.rows_cap);
+        rc = make_planes_map(&tmap[b], wb + L.off_planes + (size_t)b * L.plane_buf_bytes, L.p_pad, L.rows_cap, KB);
         if (rc) return rc;
+        if (L.nb == 3) {
+            rc = make_planes_map(&tmapB[b], wb + L.off_planes + (size_t)b * L.plane_buf_bytes, L.p_pad, L.rows_cap, KB, TILE / 2);
+            if (rc) return rc;
+        }
     }
+    if (L.nb == 3) OCM_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SM_TOTAL));
     const int vec_ok = (sizeof(T) == 4 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) ? 1 : 0;
 
     // several chunks: quantise chunk c+1 on the side stream while the MMAs of chunk c run on the caller's stream
@@ -590,12 +803,18 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
         a.inv_scale = inv_scale; a.part = part; a.status = tc_status_device_ptr();
         for (int ps = 0; ps < npass; ++ps) {
             a.pr = passes[ps];
-            rc = L.nb == 1 ? launch_gram<1>(tmap[b], a, L.ntiles * splits, stream) : launch_gram<2>(tmap[b], a, L.ntiles * splits, stream);
+            if (L.nb == 3) {
+                gram_tc2_kernel<<<(unsigned)(2 * L.ntiles * splits), NTHREADS, Cfg2::SM_TOTAL, stream>>>(tmap[b], tmapB[b], a);
+                rc = check_launch("gram_tc2_kernel");
+            } else {
+                rc = L.nb == 1 ? launch_gram<1>(tmap[b], a, L.ntiles * splits, stream) : launch_gram<2>(tmap[b], a, L.ntiles * splits, stream);
+            }
             if (rc) return rc;
         }
         if (sd) OCM_CUDA(cudaEventRecord(sd->g_done[b], stream));
     }
-    if (L.nb == 1) gram_fold_kernel<1><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
+    if (L.nb == 3) gram_fold2_kernel<<<2 * L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
+    else if (L.nb == 1) gram_fold_kernel<1><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
     else gram_fold_kernel<2><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
     rc = check_launch("gram_fold_kernel");
     if (rc) return rc;

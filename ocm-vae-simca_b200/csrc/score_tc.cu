@@ -96,7 +96,11 @@ constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_OFF_MUS = SM_OFF_BAR + 256;                           // -2^XSHIFT * mu (fp16 A-operand mode)
 constexpr size_t SM_TOTAL = SM_OFF_MUS + P_MAX * 4;
-constexpr int XSHIFT = 6;                 // fp16 A operand: y = (x - mu) * 2^6, |x - mu| < 1023 stays finite in fp16
+// fp16 operand mode: every operand is prescaled by a power of two (exact) so that its low-order terms stay clear of the
+// fp16 subnormal range, and the accumulators are scaled back (exactly) when they are read:
+constexpr int XSHIFT = 6;                 // y = (x - mu) * 2^6   finite while |x - mu| < 1023
+constexpr int PSHIFT = 10;                // P * 2^10             |P| <= 1 (orthonormal rows)
+constexpr int TSHIFT = 4;                 // t * 2^4              finite while |t| < 4094
 
 // ---------------------------------------------------------------- PTX wrappers ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,17 +143,21 @@ __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
+// Returns false when the wait was abandoned.  The caller must then stop touching barriers altogether: an arrive on a
+// barrier whose phase never completed (e.g. a second expect_tx) underflows its pending count, which the hardware
+// reports as a launch failure -- found with the injected stall.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
-        if ((spins & 0xFFu) == 0 && lds32_volatile(w.abort_addr)) break;            // someone in this CTA already gave up
+        if ((spins & 0xFFu) == 0 && lds32_volatile(w.abort_addr)) return false;     // someone in this CTA already gave up
         if (spins > w.max_polls) {
             asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(w.abort_addr), "r"(1u) : "memory");
             if (w.status) atomicExch(w.status, 1u);
-            break;
+            return false;
         }
     }
+    return true;
 }
 __device__ __forceinline__ ulonglong2 lds128(uint32_t addr) {
     ulonglong2 r;
@@ -283,6 +291,19 @@ __device__ __forceinline__ void split2_f16_pack2(f32x2 y, uint32_t& whi, uint32_
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(wlo) : "r"(r1), "r"(r0));
 }
 
+// 3-way fp16 split of two (prescaled) fp32 values: h1 = rn(x), h2 = rn(x - h1), h3 = rn(x - h1 - h2); 33 bits, or
+// 2^-25 absolute once a term is subnormal -- which is why the operands are prescaled (PSHIFT / TSHIFT below)
+__device__ __forceinline__ void split3_f16_pack(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+    const f32x2 x = pk2(__float_as_uint(x0), __float_as_uint(x1));
+    uint32_t lo;
+    split2_f16_pack2(x, w1, lo);                  // w1 = rn(x), lo = rn(x - w1) -- but we need the exact remainder for term 3
+    uint32_t h0, h1;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+        : "=r"(h0), "=r"(h1) : "r"(w1));
+    const f32x2 r = sub2(x, pk2(h0, h1));         // exact
+    split2_f16_pack2(r, w2, w3);                  // w2 = rn(r), w3 = rn(r - w2)
+}
+
 // exact 3-way bf16 split of two fp32 values, packed as the tensor core wants them (low half = lower K index):
 // b1 = top 16 bits, r1 = x - b1 (exact), b2 = top 16 bits of r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2
 __device__ __forceinline__ void split3_pack(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
@@ -303,9 +324,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (UMMA InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13), a_negate 13,
 // a_major 15, b_major 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major, bool a_is_f16 = false) {
-    // a format [7,10): 0 = F16, 1 = BF16 (kind::f16 takes the two operand formats independently)
-    return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | (1u << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_neg, bool b_mn_major, bool f16 = false) {
+    // a format [7,10) and b format [10,13): 0 = F16, 1 = BF16.  The two fields exist separately, but an MMA with A = F16
+    // from TMEM and B = BF16 from shared memory raises "illegal instruction" on the B200 (measured), so both follow `f16`.
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((a_neg ? 1u : 0u) << 13) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -338,8 +360,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
 }
 
-// F16A = the A operand of the projection is a 2-term fp16 split of the prescaled centred spectrum (kind::f16 takes the
-// formats of A and B independently: A fp16 from TMEM, B = the bf16 terms of P from shared memory); false = 3 bf16 terms.
+// F16A = fp16 operand mode: the A operand of the projection is a 2-term fp16 split of the prescaled centred spectrum
+// (six converter instructions per pair instead of nine, two TMEM stores and two MMAs per k-step instead of three), the
+// loadings and the scores are 3-term fp16 splits; false = round 1's 3-term bf16 splits everywhere.
 template <bool F16A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
@@ -399,7 +422,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         }
         uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split3_pack(v[2 * e], v[2 * e + 1], w1[e], w2[e], w3[e]);
+        for (int e = 0; e < 4; ++e) {
+            if (F16A) split3_f16_pack(v[2 * e] * (float)(1 << PSHIFT), v[2 * e + 1] * (float)(1 << PSHIFT), w1[e], w2[e], w3[e]);
+            else split3_pack(v[2 * e], v[2 * e + 1], w1[e], w2[e], w3[e]);
+        }
         // atom (64 columns) -> row = term * 16 + component (128 B) -> 16-byte chunk XOR (row % 8)
         const size_t off = (size_t)(j8 >> 3) * SM_PATOM + (size_t)c * 128 + (size_t)((j8 & 7) ^ (c & 7)) * 16;
         *reinterpret_cast<uint4*>(smem + SM_OFF_P + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
@@ -462,8 +488,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const uint32_t dbase0 = lane_addr + TM_ABUF + (uint32_t)(QCOLS * qd);
 
         // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
-        auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
-            mbar_wait(bar_full, ring_phase, wctx);
+        auto load_stage = [&](uint32_t mu_addr, f32x2* xc) -> bool {
+            if (!mbar_wait(bar_full, ring_phase, wctx)) return false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const ulonglong2 v = lds128(st + xo[i]);
@@ -474,11 +500,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
             st += (uint32_t)SM_STAGE; bar_full += 8u;
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
+            return true;
         };
 
         // same, for the fp16 A operand: y = x * 2^XSHIFT - mu * 2^XSHIFT in one packed FMA (exact scaling)
-        auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) {
-            mbar_wait(bar_full, ring_phase, wctx);
+        auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) -> bool {
+            if (!mbar_wait(bar_full, ring_phase, wctx)) return false;
             const uint32_t kx = __float_as_uint((float)(1 << XSHIFT));
             const f32x2 k2 = pk2(kx, kx);
 #pragma unroll
@@ -491,6 +518,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
             st += (uint32_t)SM_STAGE; bar_full += 8u;
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
+            return true;
         };
 
         for (int64_t k = 0; k < my_tiles; ++k) {
@@ -507,16 +535,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 continue;
             }
             const uint32_t kpar = (uint32_t)(k & 1);
+            bool gave_up = false;      // a wait of THIS thread was abandoned: it touches no barrier until the end of the tile
             // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
             uint32_t mu_addr = mu0;
 #pragma unroll 1
-            for (int chunk = 0; chunk < ns; chunk += 2) {
+            for (int chunk = 0; chunk < ns && !gave_up; chunk += 2) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     f32x2 xc[QCOLS / 2];
-                    if (F16A) load_stage_scaled(mu_addr, xc); else load_stage(mu_addr, xc);
+                    // (warp votes: tcgen05.ld / st are .sync.aligned, a warp has to take or skip them together)
+                    if (!__all_sync(0xffffffffu, F16A ? load_stage_scaled(mu_addr, xc) : load_stage(mu_addr, xc))) { gave_up = true; break; }
                     mu_addr += 4u * STAGE_COLS;
-                    mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx);                  // MMAs of the buffer's previous user retired
+                    if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx))) { gave_up = true; break; }   // MMAs of the buffer's previous user retired
                     tc_fence_after();
                     const uint32_t abase = abase0 + (uint32_t)(b * 96);
                     if (F16A) {
@@ -541,11 +571,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 }
                 aph ^= 1u;
             }
+            if (!gave_up && !__all_sync(0xffffffffu, mbar_wait(BAR(B_TREADY), kpar, wctx))) gave_up = true;
             {
             // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
-            mbar_wait(BAR(B_TREADY), kpar, wctx);
             tc_fence_after();
-            if (qd == 0) {
+            if (qd == 0 && !gave_up) {
                 float t[16];
                 {
                     // small cross products first, then the four large (1,1) partial sums, all round-to-nearest
@@ -578,7 +608,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
                     if (F16A) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) t[i] *= 1.0f / (float)(1 << XSHIFT);      // undo the prescale (exact)
+                        for (int i = 0; i < 16; ++i) t[i] *= 1.0f / (float)(1 << (XSHIFT + PSHIFT));      // undo the prescales (exact)
                     }
                 }
                 float t2 = 0.f;
@@ -597,7 +627,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 t2_row = t2;
                 uint32_t s1[8], s2[8], s3[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
+                for (int i = 0; i < 8; ++i) {
+                    if (F16A) split3_f16_pack(t[2 * i] * (float)(1 << TSHIFT), t[2 * i + 1] * (float)(1 << TSHIFT), s1[i], s2[i], s3[i]);
+                    else split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
+                }
                 tc_st8(lane_addr + TM_TS, s1);
                 tc_st8(lane_addr + TM_TS + 8, s2);
                 tc_st8(lane_addr + TM_TS + 16, s3);
@@ -612,16 +645,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             f32x2 q2 = pk2(0u, 0u);
             mu_addr = mu0;
 #pragma unroll 1
-            for (int c2 = 0; c2 < nc; ++c2) {
+            for (int c2 = 0; c2 < nc && !gave_up; ++c2) {
                 const uint32_t b = (uint32_t)c2 & 1u;
                 const uint32_t dbase = dbase0 + b * (uint32_t)D2_COLS;
 #pragma unroll
                 for (int sub = 0; sub < SUBS; ++sub) {
                     f32x2 xc[QCOLS / 2];
-                    load_stage(mu_addr, xc);
+                    if (!__all_sync(0xffffffffu, load_stage(mu_addr, xc))) { gave_up = true; break; }
                     mu_addr += 4u * STAGE_COLS;
                     if (sub == 0) {
-                        mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u, wctx);    // the chunk's six MMAs have retired
+                        if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u, wctx))) { gave_up = true; break; }   // the chunk's six MMAs have retired
                         dph ^= 1u << b;
                         tc_fence_after();
                     }
@@ -634,7 +667,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     }
 #pragma unroll
                     for (int i = 0; i < QCOLS / 2; ++i) {
-                        const f32x2 r = sub2(xc[i], pk2(v[2 * i], v[2 * i + 1]));
+                        f32x2 r;
+                        if (F16A) {          // the reconstruction was accumulated as (16 t)(1024 P): r = xc - 2^-14 D
+                            const uint32_t kd = __float_as_uint(-1.0f / (float)(1 << (TSHIFT + PSHIFT)));
+                            r = fma2(pk2(v[2 * i], v[2 * i + 1]), pk2(kd, kd), xc[i]);
+                        } else {
+                            r = sub2(xc[i], pk2(v[2 * i], v[2 * i + 1]));
+                        }
                         q2 = fma2(r, r, q2);
                     }
                 }
@@ -647,7 +686,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             {
             // combine the four column quarters of each spectrum, decide, write back
             if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
-            const bool dead = named_bar_or(2, NCONV, aborted());   // a wait of this tile gave up: none of its numbers is to be trusted
+            const bool dead = named_bar_or(2, NCONV, gave_up || aborted());   // a wait of this tile gave up: none of its numbers is to be trusted
             if (qd == 0) {
                 const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
                 if (grow < a.n) {
@@ -671,19 +710,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
             int slot = 0;
             uint32_t ring_phase = 0;
-            for (int64_t k = 0; k < my_tiles; ++k) {
+            bool stop = false;
+            for (int64_t k = 0; k < my_tiles && !stop; ++k) {
                 if (aborted()) break;
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
                 for (int w = 0; w < 2 * ns; ++w) {
                     const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
-                    mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx);           // all converters drained the slot
+                    // test hook: the producer of CTA 0 dies before its 4th stage, that stage never arrives
+                    if (a.inject && blockIdx.x == 0 && k == 0 && w == 3) { stop = true; break; }
+                    if (!mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx)) { stop = true; break; }   // all converters drained the slot
                     mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
                     const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
                     const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
-                    if (!(a.inject && blockIdx.x == 0 && k == 0 && w == 3)) {       // test hook: that stage never arrives
-                        tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
-                        tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
-                    }
+                    tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
+                    tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
                     if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
                 }
             }
@@ -699,21 +739,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         constexpr uint32_t IDESC_N48 = make_idesc(TILE_M, 48, false, false, F16A);
         constexpr uint32_t IDESC_N32 = make_idesc(TILE_M, 32, false, false, F16A);
         constexpr uint32_t IDESC_N16 = make_idesc(TILE_M, 16, false, false, F16A);
-        constexpr uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, false, true);        // B = P read MN-major
+        constexpr uint32_t IDESC2 = make_idesc(TILE_M, D2_COLS, false, true, F16A);  // B = P read MN-major
         constexpr uint32_t lbo2 = (uint32_t)SM_PATOM, sbo2 = 1024u;
         const uint32_t sP = sb + (uint32_t)SM_OFF_P;
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         uint32_t aph = 0, dph = 0;          // running phase of the A buffers (pairwise) and of MY residual buffer
-        for (int64_t k = 0; k < my_tiles; ++k) {
-            if (aborted()) break;
+        bool stop = false;                  // a wait of this warp was abandoned: no MMA, no commit from here on
+        for (int64_t k = 0; k < my_tiles && !stop; ++k) {
+            if (__any_sync(0xffffffffu, aborted())) break;
             // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
             uint32_t patom = sP;
 #pragma unroll 1
-            for (int chunk = 0; chunk < ns; chunk += 2) {
+            for (int chunk = 0; chunk < ns && !stop; chunk += 2) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    mbar_wait(BAR(B_AFULL + b), aph, wctx);
+                    if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_AFULL + b), aph, wctx))) { stop = true; break; }
                     tc_fence_after();
                     // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
                     // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
@@ -733,13 +774,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 }
                 aph ^= 1u;
             }
+            if (stop) break;
             tc_commit_elect(BAR(B_TREADY));
             // ---- reconstruction: D = T * P (chunks with buffer b == mw) -----------------------------
-            mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1), wctx);
+            if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1), wctx))) break;
             tc_fence_after();
 #pragma unroll 1
             for (int c2 = mw; c2 < nc; c2 += NMMAW) {
-                mbar_wait(BAR(B_DFREE + mw), dph ^ 1u, wctx);                     // every converter has read the buffer's previous chunk
+                if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_DFREE + mw), dph ^ 1u, wctx))) { stop = true; break; }   // every converter has read the buffer's previous chunk
                 dph ^= 1u;
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in

@@ -130,6 +130,54 @@ __device__ __forceinline__ void tc_mma_ss_i8(uint32_t d_tmem, uint64_t a_desc, u
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): one MMA spans the two CTAs of a cluster (M = 256: 128 accumulator rows in each CTA's
+// TMEM; each CTA supplies its half of A and HALF of B from its own shared memory).  Only the leader (cluster rank 0)
+// issues MMAs; TMA loads of both CTAs signal the LEADER's mbarrier (peer bit of the shared::cluster address cleared);
+// tcgen05.commit arrives on the same barrier offset in both CTAs (multicast mask 0b11).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_slot, uint32_t cols) {   // one warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar & kPeerBitMask), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_elect(uint32_t bar) {                  // whole warp, one lane issues
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_i8_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+// shared-memory matrix descriptor, 64B swizzle (layout_type 4): rows of 64 bytes, 8-row groups 512 B apart
+__host__ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (4ull << 61);
+}
+
 // shared-memory matrix descriptor, 128B swizzle (UMMA SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version = 1 [46,48), layout_type 2 = SWIZZLE_128B [61,64))
 __host__ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

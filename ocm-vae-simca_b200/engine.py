@@ -464,17 +464,44 @@ class PCAModel:
         return self.mean.to(torch.float32), self.P.to(torch.float32).contiguous()
 
 
+def _fold_covariances(X, row_sets):
+    """Covariance + mean + count of every row subset.  When the subsets are 'everything but a held-out part' of a common
+    pool (k-fold training sets), the Gram is DOWNDATED: one Gram + column sums of the pool, one small Gram per held-out
+    part, combined with weights (+1, -1) by ocm_cov_from_parts_f64 around the pool mean -- instead of
+    one full-size Gram per fold.  Anything else falls back to one covariance per subset."""
+    torch = _torch()
+    sets_h = [s.cpu().numpy() for s in row_sets]
+    pool = np.unique(np.concatenate(sets_h)) if sets_h else np.zeros(0, np.int64)
+    held = [np.setdiff1d(pool, s, assume_unique=False) for s in sets_h]
+    downdate = len(sets_h) >= 2 and all(len(np.unique(s)) == len(s) for s in sets_h) and \
+        all(0 < len(h) < len(s) for h, s in zip(held, sets_h)) and X.shape[0] < GRAM_TC_MIN_ROWS * 4
+    if not downdate:
+        out = [covariance(X, idx) for idx in row_sets]
+        return [c for c, _, _ in out], [m for _, m, _ in out], [n for _, _, n in out]
+    dev = X.device
+    pool_t = index_tensor(pool, dev)
+    s0, _, n_pool = colstats(X, pool_t)
+    shift = s0 / float(n_pool)
+    G_pool = gram(X, pool_t, shift)
+    s_pool, _, _ = colstats(X, pool_t, shift)
+    covs, means, ns = [], [], []
+    for h in held:
+        h_t = index_tensor(h, dev)
+        G_h = gram(X, h_t, shift)
+        s_h, _, _ = colstats(X, h_t, shift)
+        Cm, mean = cov_from_parts(torch.stack([G_pool, G_h]), torch.stack([s_pool, s_h]), [n_pool, len(h)], [1.0, -1.0], shift)
+        covs.append(Cm); means.append(mean); ns.append(n_pool - len(h))
+    return covs, means, ns
+
+
 def fit_pca_folds(X, row_sets, k) -> list:
-    """PCA models of several row subsets of the same matrix (CV folds): one Gram per subset through its gather
-    index, ONE batched partial eigensolve for all of them (eig_topk_subspace), full solver only for a subset that
-    did not converge.  The returned models carry a `limits.Spectrum` (k leading eigenvalues + tail power sums)
-    instead of the full eigenvalue array."""
+    """PCA models of several row subsets of the same matrix (CV folds): downdated Grams (see _fold_covariances), ONE
+    batched partial eigensolve for all of them (eig_topk_subspace), full solver only for a subset that did not converge.
+    The returned models carry a `limits.Spectrum` (k leading eigenvalues + tail power sums) instead of the full
+    eigenvalue array."""
     from .limits import Spectrum
     torch = _torch()
-    covs, means, ns = [], [], []
-    for idx in row_sets:
-        Cm, mean, n = covariance(X, idx)
-        covs.append(Cm); means.append(mean); ns.append(n)
+    covs, means, ns = _fold_covariances(X, row_sets)
     Cs = torch.stack(covs)
     w, V, tails, conv = eig_topk_subspace(Cs, k)
     w_h, tails_h, conv_h = w[:, :k].cpu().numpy(), tails.cpu().numpy(), conv.cpu().numpy()
