@@ -147,10 +147,13 @@ chol_small_kernel(const double* __restrict__ G, int kb, double* __restrict__ L, 
     for (int j = 0; j < kb; ++j) {
         // column j: L[j][j] = sqrt(G[j][j] - sum_k L[j][k]^2), L[i][j] = (G[i][j] - sum_k L[i][k] L[j][k]) / L[j][j]
         if (t == 0) {
-            double s = Ls[j][j];
+            const double gjj = Ls[j][j];
+            double s = gjj;
             for (int k = 0; k < j; ++k) s -= Ls[j][k] * Ls[j][k];
-            if (!(s > 0.0) && bad == 0) bad = j + 1;
-            Ls[j][j] = s > 0.0 ? sqrt(s) : 1.0;
+            // a pivot that is rounding noise of the diagonal entry means a (numerically) rank-deficient block
+            const bool ok = s > 1e-15 * gjj && gjj > 0.0;   // (a block of condition 1e6 still has pivots ~1e-12 gjj)
+            if (!ok && bad == 0) bad = j + 1;
+            Ls[j][j] = ok ? sqrt(s) : 1.0;
         }
         __syncthreads();
         const int i = j + 1 + t;

@@ -45,7 +45,7 @@ constexpr int MAX_CHAIN_ROWS = 32704;       // 4 products x 128 x 128 x rows < 2
 constexpr int V_LIMIT = 0x5FFFFFFF;         // clamp of the fixed-point value (top digit stays <= 96)
 constexpr int QROWS = 64;
 #ifndef OCM_GRAM_DEFAULT_MODE
-#define OCM_GRAM_DEFAULT_MODE 1
+#define OCM_GRAM_DEFAULT_MODE 3
 #endif
 //                   // the quantiser pads a chunk to a multiple of this many rows
 // NB = column blocks per CTA tile.  NB = 1: 128 x 128 tiles, four accumulators (one pass over the data for the ten
@@ -62,12 +62,18 @@ template <int NB> struct Cfg {
     static constexpr int MAX_ACC = 4 / NB;
 };
 
-struct Products {
-    int n;                  // number of (k, l) digit products in this launch
-    int nacc;               // accumulators used (each TILE * NB columns of TMEM)
-    int kmin, nload;        // digit planes kmin .. nload-1 are loaded
-    int dmin;               // weight of accumulator 0 is 256^dmin, accumulator a is 256^(dmin + a)
-    uint8_t k[16], l[16], acc[16];
+// A launch ("pass") accumulates the digit products (k, l) of weights 256^d, d in [DLO, DHI], one TMEM accumulator per
+// weight.  The pass is a TEMPLATE parameter: with the product list in a run-time table every MMA operand went through
+// R2UR and the single issuing warp needed ~100 cycles per 64-cycle MMA (all three kernel variants sat at ~60 % of the
+// MMA rate whatever their shared-memory traffic); with compile-time products the descriptors are constant offsets on
+// uniform registers.
+template <int DLO, int DHI> struct Pass {
+    static constexpr int NACC = DHI - DLO + 1;
+    static constexpr int DMIN = DLO;
+    static constexpr int KMIN = DLO > S - 1 ? DLO - (S - 1) : 0;       // lowest digit plane any product of the pass touches
+    static constexpr int KMAX = DHI < S - 1 ? DHI : S - 1;
+    static constexpr int NLOAD = KMAX - KMIN + 1;
+    static constexpr int count() { int c = 0; for (int d = DLO; d <= DHI; ++d) for (int k = 0; k < S; ++k) { const int l = d - k; if (l >= 0 && l < S) ++c; } return c; }
 };
 
 struct Args {
@@ -79,7 +85,6 @@ struct Args {
     const double* inv_scale;    // [p_pad] 2^-sc
     double* part;           // [splits][ntiles][8 NB][128][16] fp64 partial tiles, each owned by ONE CTA of a launch
     unsigned int* status;   // protocol status word (mapped host memory), see mbar_wait_bounded
-    Products pr;
 };
 
 // tile index -> (row block ti, first column block tj); NB = 2 tiles cover column blocks tj, tj + 1 with tj even
@@ -252,10 +257,12 @@ __global__ void gram_colsum_kernel(const long long* __restrict__ colsum_q, const
 }
 
 // ------------------------------------------------------------------------------------------ multiply
-template <int NB>
+template <int NB, int DLO, int DHI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Args a) {
     using C = Cfg<NB>;
+    using PS = Pass<DLO, DHI>;
+    static_assert(PS::NACC <= C::MAX_ACC, "accumulators of the pass must fit the 512 TMEM columns");
     constexpr int NSTAGE = C::NSTAGE, KB = C::KB, BOX_BYTES = C::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms are 1024-byte aligned
@@ -294,7 +301,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         // ===== TMA producer: digit planes of the tile's row block (A) and column block(s) (B) ================
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();          // every box is read by up to nt tiles: keep it in L2
-            const uint32_t bytes = (uint32_t)((diag ? 1 : 1 + NB) * (a.pr.nload - a.pr.kmin) * BOX_BYTES);
+            const uint32_t bytes = (uint32_t)((diag ? 1 : 1 + NB) * PS::NLOAD * BOX_BYTES);
             int slot = 0;
             uint32_t ph = 0;
             for (int s = 0; s < nst; ++s) {
@@ -302,10 +309,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 mbar_expect_tx(BAR_FULL(slot), bytes);
                 const uint32_t dst = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
                 const int row = (st0 + s) * KB;
-                for (int k = a.pr.kmin; k < a.pr.nload; ++k)
+#pragma unroll
+                for (int k = PS::KMIN; k <= PS::KMAX; ++k)
                     tma_load_3d(dst + (uint32_t)(k * BOX_BYTES), &tmap, ti * TILE, row, k, BAR_FULL(slot), pol);
                 if (!diag)
-                    for (int k = a.pr.kmin; k < a.pr.nload; ++k)
+#pragma unroll
+                    for (int k = PS::KMIN; k <= PS::KMAX; ++k)
 #pragma unroll
                         for (int cb = 0; cb < NB; ++cb)        // columns beyond p_pad are zero-filled by the TMA
                             tma_load_3d(dst + (uint32_t)((S + k * NB + cb) * BOX_BYTES), &tmap, (tj + cb) * TILE, row, k,
@@ -318,7 +327,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         // ===== MMA issue: warp-uniform loop, one elected lane issues ============================================
         constexpr uint32_t IDESC = make_idesc_i8(TILE, TILE * NB, true, true);
         const uint32_t b_off = diag ? 0u : (uint32_t)(S * BOX_BYTES);
-        uint32_t used = 0;
         int slot = 0;
         uint32_t ph = 0;
         bool fine = true;
@@ -327,16 +335,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tc_fence_after();
             const uint32_t base = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
             // MN-major SW128 operands: 128 columns = one 128-byte atom row, 8-row groups 1024 B apart (SBO), one K = 32
-            // MMA covers the four groups of a box; the B operand of an N = 256 MMA is two atoms BOX_BYTES apart (LBO)
+            // MMA covers four groups; the B operand of an N = 256 MMA is two atoms BOX_BYTES apart (LBO).  Descriptors
+            // of the products are constant offsets (in 16-byte units, low word) from the stage's two base descriptors.
+            const uint64_t dA = make_desc_sw128(base, BOX_BYTES, 1024);
+            const uint64_t dB = make_desc_sw128(base + b_off, BOX_BYTES, 1024);
+            const uint32_t not_first = s > 0 ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < KB / KSTEP; ++ks) {              // the next k-step starts 32 rows = 4096 B further
-                for (int m = 0; m < a.pr.n; ++m) {
-                    const uint32_t acc = a.pr.acc[m];
-                    const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * BOX_BYTES + (uint32_t)ks * 4096u, BOX_BYTES, 1024);
-                    const uint64_t db = make_desc_sw128(base + b_off + (uint32_t)a.pr.l[m] * (uint32_t)(NB * BOX_BYTES) + (uint32_t)ks * 4096u,
-                                                        BOX_BYTES, 1024);
-                    tc_mma_ss_i8(tmem + acc * (uint32_t)(TILE * NB), da, db, IDESC, (used >> acc) & 1u);
-                    used |= 1u << acc;
+#pragma unroll
+                for (int d = DLO; d <= DHI; ++d) {
+#pragma unroll
+                    for (int k = 0; k < S; ++k) {
+                        const int l = d - k;
+                        if (l < 0 || l >= S) continue;
+                        const bool opens = ks == 0 && k == (d > S - 1 ? d - (S - 1) : 0);    // first product into this accumulator
+                        tc_mma_ss_i8(tmem + (uint32_t)((d - DLO) * TILE * NB), dA + (uint64_t)((k * BOX_BYTES + ks * 4096) >> 4),
+                                     dB + (uint64_t)((l * NB * BOX_BYTES + ks * 4096) >> 4), IDESC, opens ? not_first : 1u);
+                    }
                 }
             }
             tc_commit_elect(BAR_EMPTY(slot));                   // the slot is free once these MMAs have read it
@@ -349,7 +364,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const bool ok = __all_sync(0xffffffffu, mbar_wait_bounded(bar_acc, 0, wctx, 13u));      // false: the pipeline gave up -> the tile becomes NaN
         tc_fence_after();
         const int r = 32 * q + lane;                             // row of the tile
-        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * a.pr.dmin);
+        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * PS::DMIN);
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         // partial tile layout [c16][row][16]: a warp's 32 rows x 128 B are one contiguous 4 KB run per column group
         double* tile_base = a.part + ((int64_t)split * a.ntiles + tile) * (int64_t)(TILE * TILE * NB);
@@ -359,7 +374,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             long long tsum[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) tsum[e] = 0;
-            for (int ac = 0; ac < a.pr.nacc; ++ac) {
+#pragma unroll
+            for (int ac = 0; ac < PS::NACC; ++ac) {
                 uint32_t v[16];
                 tc_ld16(lane_addr + (uint32_t)(ac * TILE * NB + 16 * c16), v);
                 tc_wait_ld();
@@ -416,9 +432,12 @@ inline int pair_count(int nt) {
     return c;
 }
 
+template <int DLO, int DHI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ Args a) {
     using C = Cfg2;
+    using PS = Pass<DLO, DHI>;
+    static_assert(PS::NACC <= 4, "accumulators of the pass must fit the 512 TMEM columns");
     constexpr int NSTAGE = C::NSTAGE, KB = C::KB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -459,8 +478,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         // ===== TMA producer (each CTA loads its own A planes and its half of the B planes) =====================
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();
-            const int nl = a.pr.nload - a.pr.kmin;
-            const uint32_t bytes_pair = (uint32_t)(2 * nl * (C::A_BOX + C::B_BOX));
+            const uint32_t bytes_pair = (uint32_t)(2 * PS::NLOAD * (C::A_BOX + C::B_BOX));
             int slot = 0;
             uint32_t ph = 0;
             for (int s = 0; s < nst; ++s) {
@@ -468,7 +486,8 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                 if (rank == 0) mbar_expect_tx(BAR_FULL(slot), bytes_pair);
                 const uint32_t dst = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
                 const int row = (st0 + s) * KB;
-                for (int k = a.pr.kmin; k < a.pr.nload; ++k) {
+#pragma unroll
+                for (int k = PS::KMIN; k <= PS::KMAX; ++k) {
                     tma_load_3d_2sm(dst + (uint32_t)(k * C::A_BOX), &tmapA, ti * TILE, row, k, BAR_FULL(slot), pol);
                     tma_load_3d_2sm(dst + (uint32_t)(S * C::A_BOX + k * C::B_BOX), &tmapB, tj * TILE + (TILE / 2) * rank, row, k,
                                     BAR_FULL(slot), pol);
@@ -481,7 +500,6 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         // ===== MMA issue: the leader only ==========================================================================
         if (rank == 0) {
             constexpr uint32_t IDESC = make_idesc_i8(2 * TILE, TILE, true, true);
-            uint32_t used = 0;
             int slot = 0;
             uint32_t ph = 0;
             bool fine = true;
@@ -489,17 +507,23 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                 if (!__all_sync(0xffffffffu, mbar_wait_bounded(BAR_FULL(slot), ph, wctx, 22u))) { fine = false; break; }
                 tc_fence_after();
                 const uint32_t base = sb + (uint32_t)slot * (uint32_t)C::STAGE_BYTES;
+                // A: MN-major SW128 (128 rows of G = 128 bytes), 8-row K groups 1024 B apart, k-step = 4096 B
+                // B: this CTA's 64 columns, MN-major SW64 (64-byte rows), 8-row K groups 512 B apart, k-step = 2048 B
+                const uint64_t dA = make_desc_sw128(base, C::A_BOX, 1024);
+                const uint64_t dB = make_desc_sw64(base + (uint32_t)(S * C::A_BOX), C::B_BOX, 512);
+                const uint32_t not_first = s > 0 ? 1u : 0u;
 #pragma unroll
                 for (int ks = 0; ks < KB / KSTEP; ++ks) {
-                    for (int m = 0; m < a.pr.n; ++m) {
-                        const uint32_t acc = a.pr.acc[m];
-                        // A: MN-major SW128 (128 rows of G = 128 bytes), 8-row K groups 1024 B apart, k-step = 4096 B
-                        const uint64_t da = make_desc_sw128(base + (uint32_t)a.pr.k[m] * C::A_BOX + (uint32_t)ks * 4096u, C::A_BOX, 1024);
-                        // B: this CTA's 64 columns, MN-major SW64 (64-byte rows), 8-row K groups 512 B apart, k-step = 2048 B
-                        const uint64_t db = make_desc_sw64(base + (uint32_t)(S * C::A_BOX) + (uint32_t)a.pr.l[m] * C::B_BOX + (uint32_t)ks * 2048u,
-                                                           C::B_BOX, 512);
-                        tc_mma_ss_i8_2sm(tmem + acc * (uint32_t)TILE, da, db, IDESC, (used >> acc) & 1u);
-                        used |= 1u << acc;
+#pragma unroll
+                    for (int d = DLO; d <= DHI; ++d) {
+#pragma unroll
+                        for (int k = 0; k < S; ++k) {
+                            const int l = d - k;
+                            if (l < 0 || l >= S) continue;
+                            const bool opens = ks == 0 && k == (d > S - 1 ? d - (S - 1) : 0);
+                            tc_mma_ss_i8_2sm(tmem + (uint32_t)((d - DLO) * TILE), dA + (uint64_t)((k * C::A_BOX + ks * 4096) >> 4),
+                                             dB + (uint64_t)((l * C::B_BOX + ks * 2048) >> 4), IDESC, opens ? not_first : 1u);
+                        }
                     }
                 }
                 tc_commit_2sm_elect(BAR_EMPTY(slot));           // frees the slot in BOTH CTAs
@@ -514,14 +538,15 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         const bool ok = __all_sync(0xffffffffu, mbar_wait_bounded(bar_acc, 0, wctx, 23u));
         tc_fence_after();
         const int r = 32 * q + lane;
-        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * a.pr.dmin);
+        const double w_i = ldexp(a.inv_scale[ti * TILE + r], 8 * PS::DMIN);
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         double* tile_base = a.part + (((int64_t)split * a.ntiles + tile) * 2 + rank) * (int64_t)(TILE * TILE);
         for (int c16 = 0; c16 < TILE / 16; ++c16) {
             long long tsum[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) tsum[e] = 0;
-            for (int ac = 0; ac < a.pr.nacc; ++ac) {
+#pragma unroll
+            for (int ac = 0; ac < PS::NACC; ++ac) {
                 uint32_t v[16];
                 tc_ld16(lane_addr + (uint32_t)(ac * TILE + 16 * c16), v);
                 tc_wait_ld();
@@ -588,28 +613,6 @@ static int make_planes_map(CUtensorMap* map, const uint8_t* planes, int p_pad, i
     return 0;
 }
 
-// products with weight 256^d, d in [dlo, dhi], one accumulator per weight
-static Products product_table(int dlo, int dhi) {
-    Products pr{};
-    pr.dmin = dlo;
-    pr.nacc = dhi - dlo + 1;
-    int kmax = 0, kmin = S;
-    for (int d = dlo; d <= dhi; ++d)
-        for (int k = 0; k < S; ++k) {
-            const int l = d - k;
-            if (l < 0 || l >= S) continue;
-            pr.k[pr.n] = (uint8_t)k; pr.l[pr.n] = (uint8_t)l; pr.acc[pr.n] = (uint8_t)(d - dlo);
-            ++pr.n;
-            if (k > kmax) kmax = k;
-            if (l > kmax) kmax = l;
-            if (k < kmin) kmin = k;
-            if (l < kmin) kmin = l;
-        }
-    pr.nload = kmax + 1;
-    pr.kmin = kmin;
-    return pr;
-}
-
 // K splits of a chunk: every (tile, split) is one CTA with its own partial tile.  Cost model in cycles: 64 NB cycles
 // per MMA, ~15 k cycles of set-up + flush per CTA; whole waves of `sms` CTAs.
 static int choose_splits(int ntiles, int nstages, int sms, int nprod, int nb) {
@@ -626,12 +629,13 @@ static int choose_splits(int ntiles, int nstages, int sms, int nprod, int nb) {
     return best_sp;
 }
 
-// kernel variant: 1 = 128 x 128 tile per CTA, 2 = 128 x 256 tile per CTA, 3 = 256 x 128 tile per CTA PAIR (cta_group::2).
-// OCM_GRAM_NB picks one for A/B runs.
+// kernel variant: 1 = 128 x 128 tile per CTA, 3 = 256 x 128 tile per CTA PAIR (cta_group::2, the default: ~10 % faster).
+// OCM_GRAM_NB=1 picks the single-CTA kernel for A/B runs.  (A 128 x 256 single-CTA variant, template NB = 2 with two
+// weights per pass, measured 1.7x SLOWER -- its low-weight passes load as much as the main pass for a third of the MMAs --
+// and is not instantiated.)
 static int column_blocks() {
     static const int nb = [] {
         const char* e = getenv("OCM_GRAM_NB");
-        if (e && e[0] == '2') return 2;
         if (e && e[0] == '3') return 3;
         if (e && e[0] == '1') return 1;
         return OCM_GRAM_DEFAULT_MODE;
@@ -648,7 +652,7 @@ static Layout workspace_layout(int64_t n, int p) {
     L.nb = column_blocks();
     L.p_pad = (p + TILE - 1) / TILE * TILE;
     L.nt = L.p_pad / TILE;
-    L.ntiles = L.nb == 1 ? tile_count<1>(L.nt) : L.nb == 2 ? tile_count<2>(L.nt) : pair_count(L.nt);   // mode 3: PAIR tiles
+    L.ntiles = L.nb == 1 ? tile_count<1>(L.nt) : pair_count(L.nt);   // mode 3: PAIR tiles
     int64_t rc = (n + QROWS - 1) / QROWS * QROWS;
     if (rc > MAX_CHAIN_ROWS) rc = MAX_CHAIN_ROWS;
     if (rc < QROWS) rc = QROWS;
@@ -693,12 +697,35 @@ static Side* side_of_device(int dev) {
     return sd;
 }
 
-template <int NB>
+template <int NB, int DLO, int DHI>
 static int launch_gram(const CUtensorMap& tmap, const Args& a, int ctas, cudaStream_t stream) {
-    auto kern = gram_tc_kernel<NB>;
+    auto kern = gram_tc_kernel<NB, DLO, DHI>;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NB>::SM_TOTAL));
     kern<<<(unsigned)ctas, NTHREADS, Cfg<NB>::SM_TOTAL, stream>>>(tmap, a);
     return check_launch("gram_tc_kernel");
+}
+template <int DLO, int DHI>
+static int launch_gram_pair(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const Args& a, int ctas, cudaStream_t stream) {
+    auto kern = gram_tc2_kernel<DLO, DHI>;
+    OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SM_TOTAL));
+    kern<<<(unsigned)ctas, NTHREADS, Cfg2::SM_TOTAL, stream>>>(tmapA, tmapB, a);
+    return check_launch("gram_tc2_kernel");
+}
+
+// one chunk: every pass of the chosen kernel variant (mode 1: 128 x 128 tiles, 2: 128 x 256 tiles, 3: CTA pairs)
+static int launch_passes(int mode, int products, const CUtensorMap& tmap, const CUtensorMap& tmapB, const Args& a, int ctas,
+                         cudaStream_t st) {
+    int rc = 0;
+    if (mode == 1) {
+        rc = launch_gram<1, 3, 6>(tmap, a, ctas, st);
+        if (!rc && products == 13) rc = launch_gram<1, 2, 2>(tmap, a, ctas, st);
+        if (!rc && products == 16) rc = launch_gram<1, 0, 2>(tmap, a, ctas, st);
+    } else {
+        rc = launch_gram_pair<3, 6>(tmap, tmapB, a, ctas, st);
+        if (!rc && products == 13) rc = launch_gram_pair<2, 2>(tmap, tmapB, a, ctas, st);
+        if (!rc && products == 16) rc = launch_gram_pair<0, 2>(tmap, tmapB, a, ctas, st);
+    }
+    return rc;
 }
 
 template <typename T>
@@ -728,25 +755,13 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
     const int sms = sm_count();
     const int64_t nchunks = (n + L.rows_cap - 1) / L.rows_cap;
 
-    // passes: which weights 256^d go into which launch (one accumulator per weight, 4 / NB accumulators per launch)
-    Products passes[4];
-    int npass = 0;
-    if (L.nb != 2) {
-        passes[npass++] = product_table(3, 6);
-        if (products == 13) passes[npass++] = product_table(2, 2);
-        if (products == 16) passes[npass++] = product_table(0, 2);
-    } else {
-        passes[npass++] = product_table(3, 4);
-        passes[npass++] = product_table(5, 6);
-        if (products >= 13) passes[npass++] = product_table(2, 2);
-        if (products == 16) passes[npass++] = product_table(0, 1);
-    }
+    const int first_pass_products = Pass<3, 6>::count();
 
     // the K split is fixed for the call (the partial buffer is indexed by it); the last, shorter chunk just has fewer stages
-    const int KB = L.nb == 2 ? Cfg<2>::KB : 64;
+    const int KB = 64;
     const int ctas_per_tile = L.nb == 3 ? 2 : 1;
     const int nstages_full = (int)(((n < L.rows_cap ? n : L.rows_cap) + KB - 1) / KB);
-    int splits = choose_splits(L.ntiles * ctas_per_tile, nstages_full, sms, passes[0].n, L.nb == 2 ? 2 : 1);
+    int splits = choose_splits(L.ntiles * ctas_per_tile, nstages_full, sms, first_pass_products, L.nb == 2 ? 2 : 1);
     if (splits > L.max_splits) splits = L.max_splits;
 
     OCM_CUDA(cudaMemsetAsync(wflags, 0, 64, stream));
@@ -765,7 +780,6 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
             if (rc) return rc;
         }
     }
-    if (L.nb == 3) OCM_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SM_TOTAL));
     const int vec_ok = (sizeof(T) == 4 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) ? 1 : 0;
 
     // several chunks: quantise chunk c+1 on the side stream while the MMAs of chunk c run on the caller's stream
@@ -801,21 +815,12 @@ int gram_tc_impl(const T* X, int64_t ldx, const int64_t* row_idx, int64_t n, int
         a.p = p; a.nt = L.nt; a.ntiles = L.ntiles; a.nstages = (rows + KB - 1) / KB;
         a.stages_per_split = (nstages_full + splits - 1) / splits;
         a.inv_scale = inv_scale; a.part = part; a.status = tc_status_device_ptr();
-        for (int ps = 0; ps < npass; ++ps) {
-            a.pr = passes[ps];
-            if (L.nb == 3) {
-                gram_tc2_kernel<<<(unsigned)(2 * L.ntiles * splits), NTHREADS, Cfg2::SM_TOTAL, stream>>>(tmap[b], tmapB[b], a);
-                rc = check_launch("gram_tc2_kernel");
-            } else {
-                rc = L.nb == 1 ? launch_gram<1>(tmap[b], a, L.ntiles * splits, stream) : launch_gram<2>(tmap[b], a, L.ntiles * splits, stream);
-            }
-            if (rc) return rc;
-        }
+        rc = launch_passes(L.nb, products, tmap[b], tmapB[b], a, L.ntiles * ctas_per_tile * splits, stream);
+        if (rc) return rc;
         if (sd) OCM_CUDA(cudaEventRecord(sd->g_done[b], stream));
     }
     if (L.nb == 3) gram_fold2_kernel<<<2 * L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
-    else if (L.nb == 1) gram_fold_kernel<1><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
-    else gram_fold_kernel<2><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
+    else gram_fold_kernel<1><<<L.ntiles, 256, 0, stream>>>(part, splits, L.nt, L.ntiles, p, colsumsq_q, inv_scale, G);
     rc = check_launch("gram_fold_kernel");
     if (rc) return rc;
     if (colsum) {

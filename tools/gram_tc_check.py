@@ -92,6 +92,12 @@ def timing(n, p, products):
     torch.cuda.synchronize()
     t0 = time.perf_counter(); Gd = engine.gram(X[:m], None, shift); torch.cuda.synchronize(); t_d = time.perf_counter() - t0
     d = torch.triu(Gt - Gd).abs().max().item() / torch.triu(Gd).abs().max().item()
+    sym = lambda G_: (torch.triu(G_) + torch.triu(G_, 1).T) / (m - 1)
+    ev_d = np.sort(engine.eigvals_sym(sym(Gd)).cpu().numpy())[::-1][:40]
+    ev_t = np.sort(engine.eigvals_sym(sym(Gt)).cpu().numpy())[::-1][:40]
+    out["eig_rel_diff_top20_vs_dmma"] = float(np.max(np.abs(ev_t[:20] - ev_d[:20]) / ev_d[:20]))
+    out["eig_rel_diff_21_40_vs_dmma"] = float(np.max(np.abs(ev_t[20:] - ev_d[20:]) / ev_d[20:]))
+    out["lambda_1_20_40"] = [float(ev_d[0]), float(ev_d[19]), float(ev_d[39])]
     out.update({"dmma_rows": m, "dmma_ms": t_d * 1e3, "dmma_tflops": m * p * (p + 1.0) / t_d / 1e12, "max_diff_vs_dmma_rel": d})
     print(json.dumps(out), flush=True)
 
