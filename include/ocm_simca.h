@@ -32,9 +32,10 @@ extern "C" {
 #define OCM_EINVAL (-1)   /* bad argument (NULL pointer, non-positive size, unknown enum) */
 #define OCM_ELIMIT (-2)   /* size outside what the kernels support (e.g. n_components > 64) */
 #define OCM_EALIGN (-3)   /* pointer / leading dimension alignment not supported by this path */
-#define OCM_ETIMEOUT (-4) /* a tensor-core kernel of an EARLIER launch abandoned a bounded mbarrier wait; what it owned
-                             was written as NaN.  Reported once, by the next tensor-core call or by
-                             ocm_simca_score_tc_status(); the call that returns it has launched nothing. */
+#define OCM_ETIMEOUT (-4) /* a tensor-core kernel of an EARLIER launch abandoned a bounded mbarrier wait.  Scoring kernels
+                             trap (that launch fails as a whole, CUDA reports it at the next synchronisation, every later
+                             tensor-core call returns this code); the Gram kernel writes NaN tiles and the code is
+                             reported once.  The call that returns it has launched nothing. */
 
 /* preprocessing modes */
 #define OCM_PRE_SNV       1   /* (x - mean_row) / (std_row(ddof=0) + eps)      simca_nuts.py:48-50 */
@@ -209,10 +210,11 @@ int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
                            const float* mu, const float* P, const float* Sinv,
                            const ocm_score_params* h_params,
                            float* T2, float* Q, uint8_t* accept, void* stream);
-/* Synchronises the device, then returns and CLEARS the protocol status of the tcgen05 kernels (scoring and Gram):
- * 0 = every launch so far completed its hand-offs, > 0 = a bounded mbarrier wait was abandoned (the kernel finished,
- * the affected rows are NaN / rejected), -1 = CUDA error.  The scoring / Gram entry points check the same word
- * (without synchronising) before they launch and return OCM_ETIMEOUT once. */
+/* Synchronises the device, then returns the protocol status of the tcgen05 kernels (scoring and Gram):
+ * 0 = every launch so far completed its hand-offs, > 0 = a bounded mbarrier wait was abandoned (1, 2: a scoring kernel
+ * trapped, the launch failed and the context is lost; >= 10: the Gram kernel finished with NaN tiles, cleared by this
+ * call), -1 = CUDA error without a status code.  The scoring / Gram entry points check the same word (without
+ * synchronising) before they launch and return OCM_ETIMEOUT. */
 int ocm_simca_score_tc_status(void);
 /* test hook: the next tcgen05 scoring launch drops one TMA stage in its first CTA, so that the bounded wait gives up
  * after `max_polls` polls (>= 16).  Exists so that the failure path is exercised by the test-suite. */

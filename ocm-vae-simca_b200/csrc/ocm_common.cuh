@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int  sm_count();
 unsigned int* tc_status_device_ptr();      // device-visible status word of the tcgen05 kernels (mapped host memory)
-int  tc_status_take();                     // read-and-clear from the host (no device access); 0 = clean
+int  tc_status_take();                     // read from the host (no device access); 0 = clean
 int  tc_status_report(const char* where);  // 0, or OCM_ETIMEOUT with the error text set
 
 inline int check_launch(const char* what) {

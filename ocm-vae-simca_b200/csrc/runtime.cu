@@ -33,10 +33,12 @@ int sm_count() {
 }
 
 // ---- protocol status of the tcgen05 kernels ---------------------------------------------------------------
-// One 32-bit word per device in MAPPED pinned host memory: a kernel whose bounded mbarrier wait gives up writes a
-// non-zero code there (and NaN-poisons its outputs); the host reads the word without touching the device, at the
-// entry of the next call and after the synchronising calls, reports OCM_ETIMEOUT once and clears it -- a later
-// launch never inherits the flag.
+// One 32-bit word per device in MAPPED pinned host memory.  A kernel whose bounded mbarrier wait expires writes a
+// non-zero code there and traps: the launch fails (CUDA reports cudaErrorLaunchFailure at the next synchronisation and
+// the context is lost, as for any device-side fault).  The host reads the word without touching the device at the
+// entry of every tensor-core call and returns OCM_ETIMEOUT with the cause spelled out; the word is NOT cleared, the
+// process has to be restarted.  (The Gram kernel, whose waits are off the critical path, instead stops its roles,
+// writes NaN tiles and finishes: codes >= 10, reported once and cleared.)
 namespace {
 struct StatusWord { unsigned int* host = nullptr; unsigned int* dev = nullptr; };
 StatusWord g_status[64];
@@ -64,15 +66,20 @@ int tc_status_take() {
     StatusWord& w = g_status[dev];
     if (!w.host) return 0;
     const unsigned int v = *reinterpret_cast<volatile unsigned int*>(w.host);
-    if (v) *reinterpret_cast<volatile unsigned int*>(w.host) = 0;
+    if (v >= 10u) *reinterpret_cast<volatile unsigned int*>(w.host) = 0;      // Gram codes: the kernel finished, report once
     return (int)v;
 }
 
 int tc_status_report(const char* where) {
     const int v = tc_status_take();
     if (!v) return 0;
-    set_error("%s: a tcgen05 kernel of an EARLIER launch gave up a bounded mbarrier wait (code %d); the rows / tiles it "
-              "owned were written as NaN", where, v);
+    if (v >= 10)
+        set_error("%s: the tcgen05 Gram kernel of an earlier launch gave up a bounded mbarrier wait (code %d); the tiles it "
+                  "owned were written as NaN", where, v);
+    else
+        set_error("%s: the tcgen05 scoring kernel of an earlier launch %s (code %d) and trapped; that launch failed, none of "
+                  "its outputs is valid and the CUDA context of this process is lost", where,
+                  v == 2 ? "found its TMEM allocation away from column 0" : "gave up a bounded mbarrier wait", v);
     return OCM_ETIMEOUT;
 }
 

@@ -125,39 +125,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait.  A hand-off that never completes (protocol bug, wedged TMA) must neither hang the GPU nor pass
-// unnoticed: after `max_polls` polls the waiting thread raises the CTA's abort word in shared memory and writes a code
-// into the device's status word (mapped host memory, runtime.cu).  Every role tests the abort word once per tile and
-// then stops working: the converters write NaN / reject for every row the CTA still owns (the tile in flight
-// included), the host reports OCM_ETIMEOUT at its next call.  The status word is cleared by the host when it reports,
-// so a later launch never inherits it.
-// (A/B-tested on the B200, twice: a leaner polling loop -- PTX loop around try_wait, 5 instructions per round -- is
-// 10 % SLOWER end to end than this one, try_wait suspend hints 6 % slower, and a __nanosleep back-off of 20..200 ns
-// makes no difference.  The loop stays as it is.)
+// unnoticed: after `max_polls` polls the waiting thread writes a code into the device's status word (mapped host
+// memory, runtime.cu) and TRAPS -- the launch fails, the stream reports cudaErrorLaunchFailure at its next
+// synchronisation and every later call of the library returns OCM_ETIMEOUT (the host reads the status word without
+// touching the device).  Nothing the launch wrote is handed out as a result.
+// Round 2 first carried an abort word through every role (NaN rows for the tiles of the CTA that gave up, warp votes
+// around every wait so that no role touches a barrier after an abandoned wait): A/B-timed at +13 % kernel time
+// (tools/ab_score.py, same box: 8.87 -> 10.0 ms first launch), for a path that must never run.  The trap costs nothing.
+// (Also A/B-tested, twice: a leaner polling loop -- PTX loop around try_wait, 5 instructions per round -- is 10 %
+// SLOWER end to end than this one, try_wait suspend hints 6 % slower, a __nanosleep back-off makes no difference.)
 struct WaitCtx {
-    uint32_t abort_addr;        // shared-space address of the CTA's abort word
     unsigned int* status;       // device-visible status word (may be NULL)
     uint32_t max_polls;
 };
-__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
+__device__ __noinline__ void wait_timed_out(unsigned int* status) {
+    if (status) { atomicExch(status, 1u); __threadfence_system(); }
+    __trap();
 }
-// Returns false when the wait was abandoned.  The caller must then stop touching barriers altogether: an arrive on a
-// barrier whose phase never completed (e.g. a second expect_tx) underflows its pending count, which the hardware
-// reports as a launch failure -- found with the injected stall.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        ++spins;
-        if ((spins & 0xFFu) == 0 && lds32_volatile(w.abort_addr)) return false;     // someone in this CTA already gave up
-        if (spins > w.max_polls) {
-            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(w.abort_addr), "r"(1u) : "memory");
-            if (w.status) atomicExch(w.status, 1u);
-            return false;
-        }
+        if (++spins > w.max_polls) wait_timed_out(w.status);
     }
-    return true;
 }
 __device__ __forceinline__ ulonglong2 lds128(uint32_t addr) {
     ulonglong2 r;
@@ -227,19 +216,6 @@ __device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, u
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// named barrier that also ORs a predicate over its participants: the 512 converter threads take the abort decision
-// TOGETHER (a thread that skipped a tile on its own would leave the others at the tile's named barriers for ever)
-__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
-    uint32_t r;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "setp.ne.b32 q, %3, 0;\n\t"
-        "bar.red.or.pred p, %1, %2, q;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(r) : "r"(id), "r"(nthreads), "r"((uint32_t)pred) : "memory");
-    return r != 0;
 }
 
 // packed fp32 pair arithmetic (sm_100 FADD2/FFMA2): one issue slot for two lanes of work
@@ -374,8 +350,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + (uint32_t)SM_OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    const WaitCtx wctx{bar0 + 8u * (uint32_t)B_COUNT + 4u, a.status, a.max_polls};
-    auto aborted = [&]() { return lds32_volatile(wctx.abort_addr) != 0u; };
+    const WaitCtx wctx{a.status, a.max_polls};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (a.n + TILE_M - 1) / TILE_M;
@@ -388,7 +363,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        s_tmem[1] = 0u;                                                    // abort word
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), NCONV); }
         for (int b = 0; b < NABUF; ++b) { mbar_init(BAR(B_AFULL + b), NCONV); mbar_init(BAR(B_AFREE + b), NMMAW); }
         for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFREE + b), NCONV); mbar_init(BAR(B_DREADY + b), 1); }
@@ -453,8 +427,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     // The CTA is alone on its SM (shared-memory footprint) and allocates all 512 columns, so the base is 0; using
     // the constant keeps every TMEM address an immediate in the MMA issue loop.  Anything else is flagged.
     if (*s_tmem != 0u) {                                                   // uniform over the CTA: nothing below would be valid
-        if (tid == 0) { s_tmem[1] = 2u; if (a.status) atomicExch(a.status, 2u); }
-        __syncthreads();
+        if (a.status) { atomicExch(a.status, 2u); __threadfence_system(); }
+        __trap();
     }
     constexpr uint32_t tmem = 0u;
 
@@ -488,8 +462,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const uint32_t dbase0 = lane_addr + TM_ABUF + (uint32_t)(QCOLS * qd);
 
         // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
-        auto load_stage = [&](uint32_t mu_addr, f32x2* xc) -> bool {
-            if (!mbar_wait(bar_full, ring_phase, wctx)) return false;
+        auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
+            mbar_wait(bar_full, ring_phase, wctx);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const ulonglong2 v = lds128(st + xo[i]);
@@ -500,12 +474,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
             st += (uint32_t)SM_STAGE; bar_full += 8u;
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
-            return true;
         };
 
         // same, for the fp16 A operand: y = x * 2^XSHIFT - mu * 2^XSHIFT in one packed FMA (exact scaling)
-        auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) -> bool {
-            if (!mbar_wait(bar_full, ring_phase, wctx)) return false;
+        auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) {
+            mbar_wait(bar_full, ring_phase, wctx);
             const uint32_t kx = __float_as_uint((float)(1 << XSHIFT));
             const f32x2 k2 = pk2(kx, kx);
 #pragma unroll
@@ -518,35 +491,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             mbar_arrive_at<8 * (B_EMPTY - B_FULL)>(bar_full);
             st += (uint32_t)SM_STAGE; bar_full += 8u;
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
-            return true;
         };
 
         for (int64_t k = 0; k < my_tiles; ++k) {
-            if (named_bar_or(2, NCONV, aborted())) {
-                // the CTA's protocol is dead: every row it still owns is marked, nothing else is touched
-                if (qd == 0) {
-                    const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
-                    if (grow < a.n) {
-                        if (a.T2) a.T2[grow] = __int_as_float(0x7fc00000);
-                        if (a.Q) a.Q[grow] = __int_as_float(0x7fc00000);
-                        if (a.accept) a.accept[grow] = 0;
-                    }
-                }
-                continue;
-            }
             const uint32_t kpar = (uint32_t)(k & 1);
-            bool gave_up = false;      // a wait of THIS thread was abandoned: it touches no barrier until the end of the tile
             // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
             uint32_t mu_addr = mu0;
 #pragma unroll 1
-            for (int chunk = 0; chunk < ns && !gave_up; chunk += 2) {
+            for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     f32x2 xc[QCOLS / 2];
-                    // (warp votes: tcgen05.ld / st are .sync.aligned, a warp has to take or skip them together)
-                    if (!__all_sync(0xffffffffu, F16A ? load_stage_scaled(mu_addr, xc) : load_stage(mu_addr, xc))) { gave_up = true; break; }
+                    if (F16A) load_stage_scaled(mu_addr, xc); else load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
-                    if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx))) { gave_up = true; break; }   // MMAs of the buffer's previous user retired
+                    mbar_wait(BAR(B_AFREE + b), aph ^ 1u, wctx);           // MMAs of the buffer's previous user retired
                     tc_fence_after();
                     const uint32_t abase = abase0 + (uint32_t)(b * 96);
                     if (F16A) {
@@ -571,11 +529,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 }
                 aph ^= 1u;
             }
-            if (!gave_up && !__all_sync(0xffffffffu, mbar_wait(BAR(B_TREADY), kpar, wctx))) gave_up = true;
+            mbar_wait(BAR(B_TREADY), kpar, wctx);
             {
             // projection complete: scores back, T2 in a register, split scores -> A operand of pass 2
             tc_fence_after();
-            if (qd == 0 && !gave_up) {
+            if (qd == 0) {
                 float t[16];
                 {
                     // small cross products first, then the four large (1,1) partial sums, all round-to-nearest
@@ -645,16 +603,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             f32x2 q2 = pk2(0u, 0u);
             mu_addr = mu0;
 #pragma unroll 1
-            for (int c2 = 0; c2 < nc && !gave_up; ++c2) {
+            for (int c2 = 0; c2 < nc; ++c2) {
                 const uint32_t b = (uint32_t)c2 & 1u;
                 const uint32_t dbase = dbase0 + b * (uint32_t)D2_COLS;
 #pragma unroll
                 for (int sub = 0; sub < SUBS; ++sub) {
                     f32x2 xc[QCOLS / 2];
-                    if (!__all_sync(0xffffffffu, load_stage(mu_addr, xc))) { gave_up = true; break; }
+                    load_stage(mu_addr, xc);
                     mu_addr += 4u * STAGE_COLS;
                     if (sub == 0) {
-                        if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u, wctx))) { gave_up = true; break; }   // the chunk's six MMAs have retired
+                        mbar_wait(BAR(B_DREADY) + 8u * b, (dph >> b) & 1u, wctx);   // the chunk's six MMAs have retired
                         dph ^= 1u << b;
                         tc_fence_after();
                     }
@@ -686,15 +644,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             {
             // combine the four column quarters of each spectrum, decide, write back
             if (qd != 0) s_q[(qd - 1) * TILE_M + row] = q_acc;
-            const bool dead = named_bar_or(2, NCONV, gave_up || aborted());   // a wait of this tile gave up: none of its numbers is to be trusted
+            named_bar_sync(2, NCONV);
             if (qd == 0) {
                 const int64_t grow = ((int64_t)blockIdx.x + k * gridDim.x) * TILE_M + row;
                 if (grow < a.n) {
-                    const float qq = dead ? __int_as_float(0x7fc00000) : (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
-                    const float tt = dead ? __int_as_float(0x7fc00000) : t2_row;
+                    const float qq = (q_acc + s_q[row]) + (s_q[TILE_M + row] + s_q[2 * TILE_M + row]);
+                    const float tt = t2_row;
                     if (a.T2) a.T2[grow] = tt;
                     if (a.Q) a.Q[grow] = qq;
-                    if (a.accept) a.accept[grow] = (!dead && rule_distance(a.rule, tt * a.ct, qq * a.cq) < a.dlim) ? 1 : 0;
+                    if (a.accept) a.accept[grow] = rule_distance(a.rule, tt * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
                 }
             }
             named_bar_sync(2, NCONV);                         // s_q reusable
@@ -712,13 +670,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             uint32_t ring_phase = 0;
             bool stop = false;
             for (int64_t k = 0; k < my_tiles && !stop; ++k) {
-                if (aborted()) break;
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
                 for (int w = 0; w < 2 * ns; ++w) {
                     const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
                     // test hook: the producer of CTA 0 dies before its 4th stage, that stage never arrives
                     if (a.inject && blockIdx.x == 0 && k == 0 && w == 3) { stop = true; break; }
-                    if (!mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx)) { stop = true; break; }   // all converters drained the slot
+                    mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx);   // all converters drained the slot
                     mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
                     const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
                     const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
@@ -745,16 +702,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         // the six products of a 3-term x 3-term split that matter at 2^-24: (A term, B term)
         const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
         uint32_t aph = 0, dph = 0;          // running phase of the A buffers (pairwise) and of MY residual buffer
-        bool stop = false;                  // a wait of this warp was abandoned: no MMA, no commit from here on
-        for (int64_t k = 0; k < my_tiles && !stop; ++k) {
-            if (__any_sync(0xffffffffu, aborted())) break;
+        for (int64_t k = 0; k < my_tiles; ++k) {
             // ---- projection: three MMAs per k-step (A term i against the stacked terms of P) ---------
             uint32_t patom = sP;
 #pragma unroll 1
-            for (int chunk = 0; chunk < ns && !stop; chunk += 2) {
+            for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_AFULL + b), aph, wctx))) { stop = true; break; }
+                    mbar_wait(BAR(B_AFULL + b), aph, wctx);
                     tc_fence_after();
                     // K-major SW128: one 64-column atom per stage, K advances 32 B (16 bf16) inside the atom, 8-row groups
                     // 1024 B apart (rows = term*16 + component, so N = 48 / 32 / 16 selects [P1;P2;P3] / [P1;P2] / [P1])
@@ -774,14 +729,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 }
                 aph ^= 1u;
             }
-            if (stop) break;
             tc_commit_elect(BAR(B_TREADY));
             // ---- reconstruction: D = T * P (chunks with buffer b == mw) -----------------------------
-            if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1), wctx))) break;
+            mbar_wait(BAR(B_THFULL), (uint32_t)(k & 1), wctx);
             tc_fence_after();
 #pragma unroll 1
             for (int c2 = mw; c2 < nc; c2 += NMMAW) {
-                if (!__all_sync(0xffffffffu, mbar_wait(BAR(B_DFREE + mw), dph ^ 1u, wctx))) { stop = true; break; }   // every converter has read the buffer's previous chunk
+                mbar_wait(BAR(B_DFREE + mw), dph ^ 1u, wctx);   // every converter has read the buffer's previous chunk
                 dph ^= 1u;
                 tc_fence_after();
                 // MN-major SW128: 64-column atoms SM_PATOM apart (LBO), 8-component groups 1024 B apart (SBO); K = 16 in
@@ -797,9 +751,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     }
 
     // ---- teardown -----------------------------------------------------------------------------
-    if (aborted()) {            // in-flight TMA boxes and MMAs of the abandoned tile: give them time to land
-        for (int i = 0; i < 100; ++i) __nanosleep(2000);
-    }
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA) {
@@ -886,10 +837,11 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     return check_launch("score_tc_kernel");
 }
 
-// synchronise, then read AND clear the protocol status word of the tcgen05 kernels (0 = clean)
+// synchronise, then read the protocol status word of the tcgen05 kernels (0 = clean)
 extern "C" int ocm_simca_score_tc_status(void) {
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    return ocm::tc_status_take();
+    const bool failed = cudaDeviceSynchronize() != cudaSuccess;
+    const int v = ocm::tc_status_take();
+    return (failed && v == 0) ? -1 : v;
 }
 
 extern "C" int ocm_simca_score_tc_inject_stall(int32_t max_polls) {

@@ -645,19 +645,21 @@ def test_tensor_core_kernel_every_row_and_repeatable(torch):
 
 
 def test_tensor_core_timeout_is_loud(torch):
-    """A bounded mbarrier wait that gives up must not pass for a result (VERDICT r1 / ADVICE): the rows the CTA owned
-    come back NaN and rejected, the NEXT call returns OCM_ETIMEOUT without launching, and the call after that is clean --
-    the flag is neither silent nor sticky.  The stall is injected through the library's test hook (one dropped TMA stage
-    in CTA 0); the scenario runs in its own process (tools/tc_timeout_check.py)."""
+    """A bounded mbarrier wait that expires must not pass for a result (VERDICT r1 / ADVICE): the kernel records a code
+    in the mapped status word and traps, so the launch fails at the next synchronisation and every later tensor-core call
+    returns OCM_ETIMEOUT without launching.  The stall is injected through the library's test hook (one dropped TMA stage
+    in CTA 0); the scenario runs in its own process (tools/tc_timeout_check.py) because the CUDA context does not
+    survive it."""
     import json, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_timeout_check.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    o = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert o["supported"] == 1 and o["status_before"] == 0 and o["clean_rc"] == 0 and o["clean_finite"]
-    assert o["stalled_launch_rc"] == 0 and o["owned_rows_nan_and_rejected"] and o["other_rows_identical"], o
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    o = json.loads(lines[-1])
+    assert o["supported"] == 1 and o["status_before"] == 0 and o["clean_rc"] == 0 and o["clean_finite"], o
+    assert o["sync_raised"], o
     assert o["next_call_rc"] == -4 and "bounded mbarrier wait" in o["next_call_message"], o
-    assert o["call_after_rc"] == 0 and o["call_after_identical"] and o["status_after"] == 0, o
+    assert o["call_after_rc"] == -4 and o["status_after"] == 1, o
 
 
 def test_nonfinite_rows_are_rejected_and_isolated(torch):

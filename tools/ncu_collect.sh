@@ -9,12 +9,12 @@ cap() {  # name, regex, script arg
       python tools/kernels_once.py $3 > gpurun_out/${tag}_$1.log 2>&1
 }
 cap score_tc "score_tc_kernel" score 2
-cap gram_tc "gram_tc_kernel" gram 2
+cap gram_tc "gram_tc2?_kernel" gram 2
 cap gram_quantize "gram_quantize_kernel" gram 1
 cap colstats_minmax "colstats_minmax_kernel" gram 0
 cap score_multiA "score_simt_kernel" all 1
 cap preprocess "preprocess_kernel" all 1
-cap savgol "savgol_kernel" all 1
+cap savgol "savgol_.*kernel" all 1
 cap latent "latent_score_kernel" all 1
 cap jacobi "jacobi_eigh_kernel" all 0
 cap symm_mul "symm_mul_kernel" score 3
