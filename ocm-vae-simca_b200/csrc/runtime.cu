@@ -66,20 +66,20 @@ int tc_status_take() {
     StatusWord& w = g_status[dev];
     if (!w.host) return 0;
     const unsigned int v = *reinterpret_cast<volatile unsigned int*>(w.host);
-    if (v >= 10u) *reinterpret_cast<volatile unsigned int*>(w.host) = 0;      // Gram codes: the kernel finished, report once
+    if (v >= 10u && v < 100u) *reinterpret_cast<volatile unsigned int*>(w.host) = 0;      // Gram codes: the kernel finished, report once
     return (int)v;
 }
 
 int tc_status_report(const char* where) {
     const int v = tc_status_take();
     if (!v) return 0;
-    if (v >= 10)
+    if (v >= 10 && v < 100)
         set_error("%s: the tcgen05 Gram kernel of an earlier launch gave up a bounded mbarrier wait (code %d); the tiles it "
                   "owned were written as NaN", where, v);
     else
         set_error("%s: the tcgen05 scoring kernel of an earlier launch %s (code %d) and trapped; that launch failed, none of "
                   "its outputs is valid and the CUDA context of this process is lost", where,
-                  v == 2 ? "found its TMEM allocation away from column 0" : "gave up a bounded mbarrier wait", v);
+                  v == 2 ? "found its TMEM allocation away from column 0" : "gave up a bounded mbarrier wait", v);      // >= 100: 100 + barrier slot of score_tc2.cu
     return OCM_ETIMEOUT;
 }
 

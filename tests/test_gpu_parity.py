@@ -659,7 +659,7 @@ def test_tensor_core_timeout_is_loud(torch):
     assert o["supported"] == 1 and o["status_before"] == 0 and o["clean_rc"] == 0 and o["clean_finite"], o
     assert o["sync_raised"], o
     assert o["next_call_rc"] == -4 and "bounded mbarrier wait" in o["next_call_message"], o
-    assert o["call_after_rc"] == -4 and o["status_after"] == 1, o
+    assert o["call_after_rc"] == -4 and o["status_after"] >= 1, o      # 1: first-generation kernel, 100 + barrier slot: cluster kernel
 
 
 def test_nonfinite_rows_are_rejected_and_isolated(torch):

@@ -41,6 +41,7 @@ stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 ref = None
 for rnd in range(a.rounds):
     for path in a.libs:
+        os.environ['OCM_SCORE_TC1'] = '1' if 'tc1' in os.path.basename(path) else '0'
         os.environ['OCM_SCORE_BF16A'] = '1' if 'bf16' in os.path.basename(path) else '0'   # read once per library at its first call
         lib = C.CDLL(os.path.abspath(path))
         fn = lib.ocm_simca_score_tc_f32
@@ -62,6 +63,13 @@ for rnd in range(a.rounds):
         chk = (float(T2[:100000].double().sum()), float(Q[:100000].double().sum()), int(acc.sum()))
         if ref is None:
             ref = chk
+            T2r, Qr = T2.clone(), Q.clone()
+        bad = torch.nonzero(((T2 - T2r).abs() > 1e-4 * T2r.abs()) | ((Q - Qr).abs() > 1e-4 * Qr.abs()) | ~torch.isfinite(Q)).flatten()
+        if bad.numel():
+            tiles = torch.unique(bad // 128)
+            print("  rows that differ from the first run:", bad.numel(), "in", tiles.numel(), "tiles; first tiles", tiles[:10].tolist(),
+                  "rows in first tile", (bad[bad // 128 == tiles[0]] % 128).tolist()[:40], "relQ", float(((Q - Qr).abs() / Qr)[bad].max()), "relT2", float(((T2 - T2r).abs() / T2r)[bad].max()),
+                  "Q/Qr of first rows", [round(float(Q[i] / Qr[i]), 2) for i in bad[:8]], "T2/T2r", [round(float(T2[i] / T2r[i]), 3) for i in bad[:8]], flush=True)
         print(json.dumps({"lib": os.path.basename(path), "round": rnd, "first": round(ms[0], 3), "min": round(min(ms), 3),
                           "median": round(sorted(ms)[len(ms) // 2], 3), "last": round(ms[-1], 3),
                           "rel_T2": abs(chk[0] - ref[0]) / ref[0], "rel_Q": abs(chk[1] - ref[1]) / ref[1], "acc": chk[2]}), flush=True)
