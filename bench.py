@@ -575,7 +575,8 @@ def main():
     elif lib.ocm_simca_score_tc_supported(rows, p, p, A, 0, C_void(X)):
         bf16a = os.environ.get("OCM_SCORE_BF16A", "0") == "1"
         kernel_name = ("score_tc_kernel<false> (tcgen05.mma kind::f16, 3-term bf16 operands, TMEM A operand, TMA ring)" if bf16a else
-                       "score_tc_kernel<true> (tcgen05.mma kind::f16, 2-term fp16 A operand from TMEM, 3-term fp16 loadings, TMA ring)")
+                       "score_tc_kernel<true> (tcgen05.mma kind::f16, 2-term fp16 A operand from TMEM prescaled from the model's x_rms, "
+                       "3-term fp16 loadings, TMA ring) + score_fixup_kernel (fp32 recomputation of rows outside the fp16 range)")
     elif lib.ocm_simca_score_rowteam_supported(rows, p, p, A, 0, C_void(X)):
         kernel_name = f"score_rowteam_kernel<{A},{p // 128 if p <= 1024 else 8},{128 if p <= 1024 else 256}> (FFMA2)"
     else:
@@ -583,7 +584,7 @@ def main():
 
     def step():
         return engine.score(X, mean32, P32, Sinv, rule="alt", ct=ct, cq=cq, dlim=lim.D_limit,
-                            force_simt=args.force_simt)
+                            force_simt=args.force_simt, x_rms=pca.x_rms)
 
     args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
     for _ in range(args.warmup):
@@ -627,7 +628,7 @@ def main():
     if not args.no_strong:
         lo, hi = odist.shard_rows(rows, rank, world)
         Xs = X[: hi - lo]                              # this rank's shard size; the rows themselves are rank-private already
-        sstep = lambda: engine.score(Xs, mean32, P32, Sinv, rule="alt", ct=ct, cq=cq, dlim=lim.D_limit, force_simt=args.force_simt)
+        sstep = lambda: engine.score(Xs, mean32, P32, Sinv, rule="alt", ct=ct, cq=cq, dlim=lim.D_limit, force_simt=args.force_simt, x_rms=pca.x_rms)
         for _ in range(3):
             sstep()
         torch.cuda.synchronize(); barrier()

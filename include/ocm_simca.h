@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCM_ABI_VERSION 1
+#define OCM_ABI_VERSION 2   /* 2: ocm_score_params.x_rms */
 
 #define OCM_EINVAL (-1)   /* bad argument (NULL pointer, non-positive size, unknown enum) */
 #define OCM_ELIMIT (-2)   /* size outside what the kernels support (e.g. n_components > 64) */
@@ -177,6 +177,12 @@ typedef struct {
     float   snv_eps;
     float   ct, cq;     /* reduced-distance scales (1/T2_limit, 1/Q_limit; dof/scale for dd) */
     float   dlim;       /* critical distance (strict <) */
+    float   x_rms;      /* 0 = unknown.  > 0: root-mean-square size of one centred element, sqrt(trace(cov) / p) of the
+                           data the model was fitted on, AND a promise that |P_ij| <= 1 (unit-norm loadings).  The
+                           tcgen05 kernel then takes its fp16 operand mode (power-of-two prescales chosen from x_rms,
+                           2-term split of the spectra): ~10 % faster, same 1e-5 parity; rows whose operands leave the
+                           fp16 range (|x - mu| > ~4000 x_rms) come out non-finite and are recomputed in fp32 by a
+                           fix-up kernel on the same stream.  With 0 the exact-at-any-scale bf16 x 3 mode runs. */
 } ocm_score_params;
 
 int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
@@ -202,14 +208,26 @@ int ocm_simca_score_rowteam_f32(const float* X, int64_t n, int32_t p, int64_t ld
                                 const ocm_score_params* h_params,
                                 float* T2, float* Q, uint8_t* accept, void* stream);
 
-/* 1 when ocm_simca_score_f32 would take the tcgen05/TMA kernel for this shape (bulk path:
- * fp32, p a multiple of the K-slice, 16-byte aligned rows), else 0. */
+/* 1 when ocm_simca_score_f32 would take a tcgen05/TMA kernel for this shape (bulk path: fp32 rows, 64 <= p <= 2048, p a
+ * multiple of 4, n_components <= 16, 16-byte aligned rows, no fused SNV, n >= 32768), else 0. */
 int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
-/* the tcgen05 kernel itself (p == 1024, n_components <= 16, 16-byte aligned rows) */
+/* the tcgen05 kernels themselves: p <= 1152 runs one CTA per 128-spectrum tile (score_tc.cu; fp16 operand mode when
+ * h_params->x_rms > 0), wider spectra the cluster kernel below with four CTAs per tile */
 int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
                            const float* mu, const float* P, const float* Sinv,
                            const ocm_score_params* h_params,
                            float* T2, float* Q, uint8_t* accept, void* stream);
+/* cluster kernel (score_tc2.cu): the wavelengths of a tile are split over 1 / 2 / 4 CTAs of a thread-block cluster
+ * (<= 512 each, p <= 2048), both passes run concurrently, partial scores meet through distributed shared memory.
+ * inject_polls: 0, or the bounded-wait limit of a launch whose first CTA drops one TMA stage (test hook). */
+int ocm_simca_score_tc2_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                            const float* mu, const float* P, const float* Sinv,
+                            const ocm_score_params* h_params,
+                            float* T2, float* Q, uint8_t* accept, int32_t inject_polls, void* stream);
+/* bring-up aid: copies the 16 words of the mapped protocol status block (word 0 = status, the rest a role trace when
+ * the library was built with OCM_TC2_TRACE) */
+int ocm_simca_score_tc_debug_words(uint32_t* out16);
 /* Synchronises the device, then returns the protocol status of the tcgen05 kernels (scoring and Gram):
  * 0 = every launch so far completed its hand-offs, > 0 = a bounded mbarrier wait was abandoned (1, 2: a scoring kernel
  * trapped, the launch failed and the context is lost; >= 10: the Gram kernel finished with NaN tiles, cleared by this

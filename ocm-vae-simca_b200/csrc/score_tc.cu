@@ -99,10 +99,11 @@ constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_OFF_MUS = SM_OFF_BAR + 256;                           // -2^XSHIFT * mu (fp16 A-operand mode)
 constexpr size_t SM_TOTAL = SM_OFF_MUS + P_MAX * 4;
 // fp16 operand mode: every operand is prescaled by a power of two (exact) so that its low-order terms stay clear of the
-// fp16 subnormal range, and the accumulators are scaled back (exactly) when they are read:
-constexpr int XSHIFT = 6;                 // y = (x - mu) * 2^6   finite while |x - mu| < 1023
-constexpr int PSHIFT = 10;                // P * 2^10             |P| <= 1 (orthonormal rows)
-constexpr int TSHIFT = 4;                 // t * 2^4              finite while |t| < 4094
+// fp16 subnormal range, and the accumulators are scaled back (exactly) when they are read.  The spectra and the scores
+// are scaled from the caller's x_rms (ocm_score_params): y = (x - mu) 2^xs with x_rms 2^xs in (8, 16] (finite up to
+// ~4000 x_rms), t 2^ts with sqrt(p) x_rms 2^ts in (32, 64]; the loadings by a fixed 2^10 (|P| <= 1, promised with x_rms).
+// Whatever leaves the fp16 range turns into inf / NaN distances, which the fix-up kernel below recomputes in fp32.
+constexpr int PSHIFT = 10;
 
 struct Args {
     int64_t n;
@@ -115,6 +116,7 @@ struct Args {
     uint32_t max_polls;       // bound of every mbarrier wait
     int inject;               // test hook: CTA 0 drops one TMA stage of its first tile
     uint32_t zero;            // always 0, see mbar_arrive_at_after
+    float kx, kt;             // fp16 mode: 2^xs, 2^ts (exact powers of two)
 };
 
 // mbarrier slots
@@ -198,7 +200,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     for (int i = tid; i < ns * STAGE_COLS; i += NTHREADS) {
         const float m = i < a.p ? a.mu[i] : 0.f;
         s_mu[i] = m;
-        if (F16A) reinterpret_cast<float*>(smem + SM_OFF_MUS)[i] = -m * (float)(1 << XSHIFT);
+        if (F16A) reinterpret_cast<float*>(smem + SM_OFF_MUS)[i] = -m * a.kx;
     }
     for (int i = tid; i < NCOMP * NCOMP; i += NTHREADS) {
         const int r = i / NCOMP, c = i % NCOMP;
@@ -272,7 +274,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         // same, for the fp16 A operand: y = x * 2^XSHIFT - mu * 2^XSHIFT in one packed FMA (exact scaling)
         auto load_stage_scaled = [&](uint32_t mu_addr, f32x2* y) {
             mbar_wait(bar_full, ring_phase, wctx);
-            const uint32_t kx = __float_as_uint((float)(1 << XSHIFT));
+            const uint32_t kx = __float_as_uint(a.kx);
             const f32x2 k2 = pk2(kx, kx);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -363,7 +365,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     for (int i = 0; i < 16; ++i) t[i] = (t[i] + (__uint_as_float(m0[i]) + __uint_as_float(m1[i]))) + cross[i];
                     if (F16A) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) t[i] *= 1.0f / (float)(1 << (XSHIFT + PSHIFT));      // undo the prescales (exact)
+                        for (int i = 0; i < 16; ++i) t[i] *= 1.0f / (a.kx * (float)(1 << PSHIFT));      // undo the prescales (exact)
                     }
                 }
                 float t2 = 0.f;
@@ -383,7 +385,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 uint32_t s1[8], s2[8], s3[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (F16A) split3_f16_pack(t[2 * i] * (float)(1 << TSHIFT), t[2 * i + 1] * (float)(1 << TSHIFT), s1[i], s2[i], s3[i]);
+                    if (F16A) split3_f16_pack(t[2 * i] * a.kt, t[2 * i + 1] * a.kt, s1[i], s2[i], s3[i]);
                     else split3_pack(t[2 * i], t[2 * i + 1], s1[i], s2[i], s3[i]);
                 }
                 tc_st8(lane_addr + TM_TS, s1);
@@ -423,8 +425,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
 #pragma unroll
                     for (int i = 0; i < QCOLS / 2; ++i) {
                         f32x2 r;
-                        if (F16A) {          // the reconstruction was accumulated as (16 t)(1024 P): r = xc - 2^-14 D
-                            const uint32_t kd = __float_as_uint(-1.0f / (float)(1 << (TSHIFT + PSHIFT)));
+                        if (F16A) {          // the reconstruction was accumulated as (16 t)(1024 P): r = xc - D / (2^ts 2^10)
+                            const uint32_t kd = __float_as_uint(-1.0f / (a.kt * (float)(1 << PSHIFT)));
                             r = fma2(pk2(v[2 * i], v[2 * i + 1]), pk2(kd, kd), xc[i]);
                         } else {
                             r = sub2(xc[i], pk2(v[2 * i], v[2 * i + 1]));
@@ -590,6 +592,65 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, i
 }  // namespace tc
 }  // namespace ocm
 
+// ---- fix-up of the fp16 operand mode -------------------------------------------------------------------------------
+// Scans T2 / Q (8 bytes per row, coalesced) and recomputes in plain fp32 every row whose distances are not finite: an
+// operand that left the fp16 range, or a spectrum that held NaN / inf to begin with (which then comes out NaN again,
+// rejected, like the reference).  A warp takes 32 rows at a time and works together on each flagged one.
+namespace ocm {
+namespace tc {
+__global__ void __launch_bounds__(256) score_fixup_kernel(const float* __restrict__ X, int64_t n, int p, int64_t ldx,
+                                                          const float* __restrict__ mu, const float* __restrict__ P,
+                                                          const float* __restrict__ Sinv, int A, int rule, float ct, float cq,
+                                                          float dlim, float* T2, float* Q, uint8_t* accept) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t base = warp * 32; base < n; base += nwarps * 32) {
+        const int64_t i = base + lane;
+        const bool flagged = i < n && !(isfinite(T2[i]) && isfinite(Q[i]));
+        unsigned todo = __ballot_sync(0xffffffffu, flagged);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = base + l;
+            const float* x = X + r * ldx;
+            float t[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = 0.f;
+            for (int j = lane; j < p; j += 32) {
+                const float xc = x[j] - mu[j];
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c < A) t[c] = fmaf(xc, P[(size_t)c * p + j], t[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = warp_sum(t[c]);
+            float q = 0.f;
+            for (int j = lane; j < p; j += 32) {
+                float rj = x[j] - mu[j];
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c < A) rj = fmaf(-t[c], P[(size_t)c * p + j], rj);
+                q = fmaf(rj, rj, q);
+            }
+            q = warp_sum(q);
+            float t2 = 0.f;
+            for (int a = 0; a < A; ++a) {
+                float sa = 0.f;
+                for (int b = 0; b < A; ++b) sa = fmaf(Sinv[a * A + b], t[b], sa);
+                t2 = fmaf(sa, t[a], t2);
+            }
+            if (lane == 0) {
+                T2[r] = t2;
+                Q[r] = q;
+                if (accept) accept[r] = rule_distance(rule, t2 * ct, q * cq) < dlim ? 1 : 0;
+            }
+        }
+    }
+}
+}  // namespace tc
+}  // namespace ocm
+
 static std::atomic<int> g_inject_polls{0};     // test hook, see ocm_simca_score_tc_inject_stall
 
 // second-generation kernel (score_tc2.cu): concurrent passes, wavelengths split over a CTA cluster; p <= 1024
@@ -604,7 +665,7 @@ extern "C" int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int
 extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X) {
     static const bool disabled = [] { const char* e = getenv("OCM_DISABLE_TC"); return e && e[0] == '1'; }();
     if (disabled) return 0;
-    if (ocm_simca_score_tc2_supported(n, p, ldx, A, snv, X)) return 1;
+    if (p > ocm::tc::P_MAX) return n >= 32768 ? ocm_simca_score_tc2_supported(n, p, ldx, A, snv, X) : 0;
     if (snv || p < 64 || p > ocm::tc::P_MAX || (p & 3) || A < 1 || A > ocm::tc::NCOMP) return 0;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
     if (n < 32768 || n >= (1ll << 31) - ocm::tc::TILE_M) return 0;
@@ -617,8 +678,9 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     using namespace ocm;
     if (n == 0) return 0;
     OCM_REQUIRE(X && mu && P && Sinv && hp, OCM_EINVAL, "NULL buffer");
-    static const bool tc1_only = [] { const char* e = getenv("OCM_SCORE_TC1"); return e && e[0] == '1'; }();
-    if (!tc1_only && p <= 1024)
+    // OCM_SCORE_TC2=1: the cluster kernel (score_tc2.cu) for p <= 1024 -- measured ~10 % behind this one, kept opt-in
+    static const bool use_tc2 = [] { const char* e = getenv("OCM_SCORE_TC2"); return e && e[0] == '1'; }();
+    if ((use_tc2 && p <= 1024) || p > tc::P_MAX)        // wider than this kernel's loadings buffer: clusters of four
         return ocm_simca_score_tc2_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, g_inject_polls.exchange(0), stream);
     OCM_REQUIRE(p >= 64 && p <= tc::P_MAX && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc::NCOMP && !hp->snv, OCM_ELIMIT,
                 "tensor-core path needs 64 <= p <= 1152 (multiple of 4), n_components <= 16, no fused SNV");
@@ -632,16 +694,29 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     if (rc) return rc;
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0, 0u};
-    // OCM_SCORE_BF16A=1 keeps the 3-term bf16 A operand of round 1 (A/B runs); default: 2-term fp16 A operand
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f};
+    // fp16 operand mode: only when the caller states the scale of the data (x_rms) and asks for both distances (the
+    // fix-up kernel finds out-of-range rows by their non-finite T2 / Q).  OCM_SCORE_BF16A=1 forces the bf16 x 3 mode.
     static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();
-    auto kern = bf16a ? tc::score_tc_kernel<false> : tc::score_tc_kernel<true>;
+    const bool f16 = !bf16a && hp->x_rms > 0.f && isfinite(hp->x_rms) && T2 && Q;
+    if (f16) {
+        int e = 0;
+        frexpf(hp->x_rms, &e);                                     // x_rms = m 2^e, m in [0.5, 1)
+        a.kx = ldexpf(1.0f, 4 - e);                                // x_rms kx in [8, 16)
+        frexpf(hp->x_rms * sqrtf((float)p), &e);
+        a.kt = ldexpf(1.0f, 6 - e);                                // |xc| of a typical row times kt in [32, 64)
+    }
+    auto kern = f16 ? tc::score_tc_kernel<true> : tc::score_tc_kernel<false>;
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
     int64_t blocks = sm_count();
     if (blocks > ntiles) blocks = ntiles;
     kern<<<(unsigned)blocks, tc::NTHREADS, tc::SM_TOTAL, (cudaStream_t)stream>>>(tmap, a);
-    return check_launch("score_tc_kernel");
+    rc = check_launch("score_tc_kernel");
+    if (rc || !f16) return rc;
+    tc::score_fixup_kernel<<<(unsigned)(2 * sm_count()), 256, 0, (cudaStream_t)stream>>>(X, n, p, ldx, mu, P, Sinv, hp->A, hp->rule, hp->ct,
+                                                                                      hp->cq, hp->dlim, T2, Q, accept);
+    return check_launch("score_fixup_kernel");
 }
 
 // synchronise, then read the protocol status word of the tcgen05 kernels (0 = clean)

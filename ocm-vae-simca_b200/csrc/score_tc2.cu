@@ -44,7 +44,8 @@ constexpr int STAGE_COLS = 64;            // pass-1 stage = one 128-byte bf16 sw
 constexpr int BOX_COLS = 32;              // TMA box: 128 rows x 32 floats (128 B rows, SWIZZLE_128B)
 constexpr int NS_MAX = 8;                 // stages per CTA slice (512 wavelengths)
 constexpr int R1 = 3;                     // ring 1: stages
-constexpr int R2 = 4;                     // ring 2: boxes (64 KB in flight: three boxes left pass 2 waiting for L2 46 % of its time)
+constexpr int R2MAX = 4;                  // ring 2: boxes (64 KB in flight: three boxes left pass 2 waiting for L2 46 % of its time);
+                                          // three for clusters of four, whose exchange buffers take the room
 constexpr int NC1 = 256, NC2 = 256, NCT = 128;       // pass-1 converters, pass-2 converters (two groups), score threads
 constexpr int W_C2 = NC1 / 32, W_CT = W_C2 + NC2 / 32, W_TMA1 = W_CT + NCT / 32, W_TMA2 = W_TMA1 + 1, W_MMAP = W_TMA1 + 2,
               W_MMAR = W_TMA1 + 3;
@@ -66,17 +67,18 @@ constexpr size_t SM_STAGE = 2 * SM_BOX;
 constexpr size_t XSLOT = (size_t)TILE_M * NCOMP * 4;            // 8192: partial scores of one peer, [4 comps][row] float4
 constexpr size_t SM_OFF_P = 0;
 constexpr size_t SM_OFF_R1 = NS_MAX * SM_PATOM;                 // 49152 (1024-aligned)
-constexpr size_t SM_OFF_R2 = SM_OFF_R1 + R1 * SM_STAGE;
-constexpr size_t SM_OFF_MU = SM_OFF_R2 + R2 * SM_BOX;
+constexpr size_t SM_OFF_MU = SM_OFF_R1 + R1 * SM_STAGE;
 constexpr size_t SM_OFF_S = SM_OFF_MU + NS_MAX * STAGE_COLS * 4;
 constexpr size_t SM_OFF_T2 = SM_OFF_S + NCOMP * NCOMP * 4;      // [2 parities][128] T2 of the tile, CT -> C2
 constexpr size_t SM_OFF_Q = SM_OFF_T2 + 2 * TILE_M * 4;         // [2 parities][128] partial Q of C2 group 1
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + 2 * TILE_M * 4;
 constexpr size_t SM_OFF_X = SM_OFF_BAR + 320;                   // [C-1 peers] XSLOT (one tile at a time, credit: XFREE), then [2][C-1][128] floats of Q
-template <int C> constexpr size_t sm_total() { return SM_OFF_X + (size_t)(C - 1) * (XSLOT + 2 * TILE_M * 4); }
-static_assert(SM_OFF_R1 % 1024 == 0 && SM_OFF_R2 % 1024 == 0 && sm_total<2>() <= 232448, "shared memory budget");
+template <int C> __host__ __device__ constexpr int r2_slots() { return C >= 4 ? 3 : R2MAX; }
+template <int C> __host__ __device__ constexpr size_t off_r2() { return (SM_OFF_X + (size_t)(C - 1) * (XSLOT + 2 * TILE_M * 4) + 1023) / 1024 * 1024; }   // ring 2 (1024-byte aligned boxes)
+template <int C> __host__ __device__ constexpr size_t sm_total() { return off_r2<C>() + (size_t)r2_slots<C>() * SM_BOX; }
+static_assert(SM_OFF_R1 % 1024 == 0 && sm_total<1>() <= 232448 && sm_total<2>() <= 232448 && sm_total<4>() <= 232448, "shared memory budget");
 
-enum { B_FULL1 = 0, B_EMPTY1 = B_FULL1 + R1, B_FULL2 = B_EMPTY1 + R1, B_EMPTY2 = B_FULL2 + R2, B_AFULL = B_EMPTY2 + R2,
+enum { B_FULL1 = 0, B_EMPTY1 = B_FULL1 + R1, B_FULL2 = B_EMPTY1 + R1, B_EMPTY2 = B_FULL2 + R2MAX, B_AFULL = B_EMPTY2 + R2MAX,
        B_AFREE = B_AFULL + 2, B_TREADY = B_AFREE + 2, B_TFREE, B_THFULL, B_C2DONE = B_THFULL + 2, B_DREADY = B_C2DONE + 2,
        B_DFREE = B_DREADY + 2, B_XFULL = B_DFREE + 2, B_XFREE, B_QFULL, B_T2RDY = B_QFULL + 2, B_COUNT = B_T2RDY + 2 };
 // words after the barriers: TMEM base, pass-2 progress (stages consumed by C2 group 0), tiles whose pass 1 has begun
@@ -229,7 +231,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < R1; ++s) { mbar_init(BAR(B_FULL1 + s), 1); mbar_init(BAR(B_EMPTY1 + s), NC1); }
-        for (int s = 0; s < R2; ++s) { mbar_init(BAR(B_FULL2 + s), 1); mbar_init(BAR(B_EMPTY2 + s), NC2); }
+        for (int s = 0; s < R2MAX; ++s) { mbar_init(BAR(B_FULL2 + s), 1); mbar_init(BAR(B_EMPTY2 + s), NC2); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(BAR(B_AFULL + b), NC1); mbar_init(BAR(B_AFREE + b), 1);
             mbar_init(BAR(B_DREADY + b), 1); mbar_init(BAR(B_DFREE + b), NC2);
@@ -366,12 +368,12 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const int row = 32 * (warp & 3) + lane;
         const uint32_t h = (uint32_t)(warp - W_C2) >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        const uint32_t ring0 = sb + (uint32_t)SM_OFF_R2 + (uint32_t)row * 128u;
+        const uint32_t ring0 = sb + (uint32_t)off_r2<C>() + (uint32_t)row * 128u;
         uint32_t xo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) xo[i] = (uint32_t)(((4 * (int)h + i) ^ (row & 7)) << 4);
         const uint32_t mu0 = sb + (uint32_t)SM_OFF_MU + 4u * 16u * h;
-        const uint32_t bar_full0 = BAR(B_FULL2), bar_full_end = BAR(B_FULL2 + R2);
+        const uint32_t bar_full0 = BAR(B_FULL2), bar_full_end = BAR(B_FULL2 + r2_slots<C>());
         uint32_t st = ring0, bar_full = bar_full0, ring_phase = 0;
         uint32_t db = 0, dph = 0;               // reconstruction buffer of the next chunk, parity of its current use
         const uint32_t qbuf0 = sb + (uint32_t)SM_OFF_X + (uint32_t)(C - 1) * (uint32_t)XSLOT;              // [par][slot][row] float
@@ -620,9 +622,9 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 for (int j = 0; j < 2 * ns; ++j) {
                     mbar_wait_s<64>(BAR(B_EMPTY2 + slot), ring_phase ^ 1u, wctx, bar0);
                     mbar_expect_tx(BAR(B_FULL2 + slot), (uint32_t)SM_BOX);
-                    tma_load_2d(sb + (uint32_t)SM_OFF_R2 + (uint32_t)slot * (uint32_t)SM_BOX, &tmap, col0 + j * BOX_COLS, row0,
+                    tma_load_2d(sb + (uint32_t)off_r2<C>() + (uint32_t)slot * (uint32_t)SM_BOX, &tmap, col0 + j * BOX_COLS, row0,
                                 BAR(B_FULL2 + slot), pol_stream);
-                    if (++slot == R2) { slot = 0; ring_phase ^= 1u; }
+                    if (++slot == r2_slots<C>()) { slot = 0; ring_phase ^= 1u; }
                     TC2_TRACE(6, (k << 8) | (j + 1));
                 }
             }
@@ -775,15 +777,12 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t stream) {
 }  // namespace tc2
 }  // namespace ocm
 
-// shape gate: fp32 rows, 64 <= p <= 1024 (one or two CTAs of <= 512 wavelengths per tile), n_components <= 16,
-// 16-byte aligned rows, no fused SNV, enough rows to fill the machine.  OCM_SCORE_TC1=1 keeps the first-generation
-// kernel (A/B runs).
+// shape gate of the cluster kernel: fp32 rows, 64 <= p <= 2048 (one, two or four CTAs of <= 512 wavelengths per tile),
+// n_components <= 16, 16-byte aligned rows, no fused SNV
 extern "C" int ocm_simca_score_tc2_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X) {
-    static const bool off = [] { const char* e = getenv("OCM_SCORE_TC1"); return e && e[0] == '1'; }();
-    if (off) return 0;
-    if (snv || p < 64 || p > 2 * ocm::tc2::NS_MAX * ocm::tc2::STAGE_COLS || (p & 3) || A < 1 || A > ocm::tc2::NCOMP) return 0;
+    if (snv || p < 64 || p > 4 * ocm::tc2::NS_MAX * ocm::tc2::STAGE_COLS || (p & 3) || A < 1 || A > ocm::tc2::NCOMP) return 0;
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
-    if (n < 32768 || n >= (1ll << 31) - ocm::tc2::TILE_M) return 0;
+    if (n >= (1ll << 31) - ocm::tc2::TILE_M) return 0;
     return 1;
 }
 
@@ -793,8 +792,8 @@ extern "C" int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int
     using namespace ocm;
     if (n == 0) return 0;
     OCM_REQUIRE(X && mu && P && Sinv && hp, OCM_EINVAL, "NULL buffer");
-    OCM_REQUIRE(p >= 64 && p <= 2 * tc2::NS_MAX * tc2::STAGE_COLS && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc2::NCOMP && !hp->snv,
-                OCM_ELIMIT, "cluster tensor-core path needs 64 <= p <= 1024 (multiple of 4), n_components <= 16, no fused SNV");
+    OCM_REQUIRE(p >= 64 && p <= 4 * tc2::NS_MAX * tc2::STAGE_COLS && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc2::NCOMP && !hp->snv,
+                OCM_ELIMIT, "cluster tensor-core path needs 64 <= p <= 2048 (multiple of 4), n_components <= 16, no fused SNV");
     OCM_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0,
                 OCM_EALIGN, "X rows and P must be 16-byte aligned");
     OCM_REQUIRE(n < (1ll << 31) - tc2::TILE_M, OCM_ELIMIT, "row count must fit the 32-bit TMA coordinate");
@@ -804,7 +803,7 @@ extern "C" int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int
     rc = tc2::make_tensor_map(&tmap, X, n, p, ldx);
     if (rc) return rc;
     const int stages = (p + tc2::STAGE_COLS - 1) / tc2::STAGE_COLS;
-    const int C = stages > tc2::NS_MAX ? 2 : 1;
+    const int C = stages > 2 * tc2::NS_MAX ? 4 : stages > tc2::NS_MAX ? 2 : 1;
     const int ns = (stages + C - 1) / C;
     static const int env_lead = [] { const char* e = getenv("OCM_TC2_LEAD"); return e ? atoi(e) : 0; }();   // in stages (experiments)
     static const int env_pol = [] { const char* e = getenv("OCM_TC2_POL"); return e ? atoi(e) : 0; }();
@@ -812,7 +811,7 @@ extern "C" int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int
     if (lead < ns + 1) lead = ns + 1;                 // pass 2 of a tile needs ALL of its pass 1: anything less deadlocks
     tc2::Args a{n, p, ns, mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
                 tc_status_device_ptr(), inject_polls > 0 ? (uint32_t)inject_polls : (1u << 22), inject_polls > 0 ? 1 : 0, lead, env_pol, 0u};
-    return C == 2 ? tc2::launch<2>(tmap, a, (cudaStream_t)stream) : tc2::launch<1>(tmap, a, (cudaStream_t)stream);
+    return C == 4 ? tc2::launch<4>(tmap, a, (cudaStream_t)stream) : C == 2 ? tc2::launch<2>(tmap, a, (cudaStream_t)stream) : tc2::launch<1>(tmap, a, (cudaStream_t)stream);
 }
 
 extern "C" int ocm_simca_score_tc_debug_words(uint32_t* out16) {

@@ -458,6 +458,7 @@ class PCAModel:
     P: "object"           # torch f64 [A, p]  (rows sign-normalised)
     eigs_all: np.ndarray  # host f64 [min(n, p)]  explained variances, descending
     n_samples: int
+    x_rms: float = 0.0    # sqrt(trace(cov) / p): size of one centred element (ocm_score_params.x_rms; 0 = unknown)
 
     def arrays32(self):
         torch = _torch()
@@ -551,6 +552,7 @@ def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False, gram_path="au
     from .limits import LazySpectrum
     Cm, mean, n = covariance(X, row_idx, group, gram_path=gram_path, products=products, timer=timer)
     p = X.shape[1]
+    x_rms = float(np.sqrt(max(float(_torch().diagonal(Cm).sum()), 0.0) / p))
     if not full_spectrum and k < p:
         w, V, tails, conv = eig_topk_subspace(Cm.unsqueeze(0), k, tol=1e-13, max_iter=90)
         if timer is not None:
@@ -560,21 +562,24 @@ def fit_pca(X, row_idx=None, k=2, group=None, full_spectrum=False, gram_path="au
             sign_normalise_(P)
             lam = np.maximum(w[0, :k].cpu().numpy(), 0.0)
             spec = LazySpectrum(lam, np.maximum(tails[0].cpu().numpy(), 0.0), lambda: _full_spectrum(Cm, n, p))
-            return PCAModel(mean=mean, P=P, eigs_all=spec, n_samples=n)
+            return PCAModel(mean=mean, P=P, eigs_all=spec, n_samples=n, x_rms=x_rms)
     evals, evecs = eigh_topk(Cm, k)
     m = min(n, p)
     eigs = evals[:m].clamp_min(0.0).cpu().numpy()
     if n <= p:
         eigs[n - 1:] = 0.0     # rank n-1: the reference's trailing values are ~1e-30 noise
-    return PCAModel(mean=mean, P=evecs, eigs_all=eigs, n_samples=n)
+    return PCAModel(mean=mean, P=evecs, eigs_all=eigs, n_samples=n, x_rms=x_rms)
 
 
 # ------------------------------------------------------------------------------------------
 # fused scoring
 # ------------------------------------------------------------------------------------------
 def score(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=False, snv_eps=1e-8,
-          want_scores=False, force_simt=False):
+          want_scores=False, force_simt=False, x_rms=0.0):
     """Fused T2 / Q / accept for the rows of X against one model.
+
+    x_rms (PCAModel.x_rms of the model's fit; 0 = unknown) lets the tcgen05 kernel use its faster fp16 operand mode, see
+    ocm_score_params in include/ocm_simca.h.
 
     X: CUDA tensor [n,p] fp32 or fp64.  mean [p], P [A,p], Sinv [A,A] any float dtype on the
     device.  Returns (T2, Q, accept[, scores]) as device tensors (fp32, fp32, uint8[, fp32])."""
@@ -588,7 +593,7 @@ def score(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=Fal
     acc = torch.empty(n, dtype=torch.uint8, device=dev)
     sc = torch.empty((n, A), dtype=torch.float32, device=dev) if want_scores else None
     prm = native.ScoreParams(A=A, rule=RULES[rule] if isinstance(rule, str) else int(rule), snv=int(bool(snv)),
-                             snv_eps=float(snv_eps), ct=float(ct), cq=float(cq), dlim=float(dlim))
+                             snv_eps=float(snv_eps), ct=float(ct), cq=float(cq), dlim=float(dlim), x_rms=float(x_rms or 0.0))
     P32 = P.to(torch.float32).contiguous()
     S32 = Sinv.to(torch.float32).contiguous()
     if X.dtype == torch.float64:

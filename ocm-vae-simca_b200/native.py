@@ -80,7 +80,7 @@ def build(force=False, verbose=False):
 
 class ScoreParams(C.Structure):
     _fields_ = [("A", C.c_int32), ("rule", C.c_int32), ("snv", C.c_int32), ("snv_eps", C.c_float),
-                ("ct", C.c_float), ("cq", C.c_float), ("dlim", C.c_float)]
+                ("ct", C.c_float), ("cq", C.c_float), ("dlim", C.c_float), ("x_rms", C.c_float)]
 
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
@@ -120,6 +120,10 @@ SIGNATURES = {
                                               _vp, _vp, _vp, _vp]),
     "ocm_simca_score_tc_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                          _vp, _vp, _vp, _vp]),
+    "ocm_simca_score_tc2_supported": (C.c_int, [_i64, _i32, _i64, _i32, _i32, _vp]),
+    "ocm_simca_score_tc2_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
+                                          _vp, _vp, _vp, _i32, _vp]),
+    "ocm_simca_score_tc_debug_words": (C.c_int, [_vp]),
     "ocm_simca_score_tc_status": (C.c_int, []),
     "ocm_simca_score_tc_inject_stall": (C.c_int, [_i32]),
     "ocm_simca_host_release": (C.c_int, []),

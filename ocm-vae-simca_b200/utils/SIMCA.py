@@ -260,7 +260,7 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         lim = info["_limits"]
         ct, cq = lim.reduced_scales(self.type)
         return engine.score(Xd, info["_pca"].mean, info["_pca"].P, info["_Sinv"], rule=self.type,
-                            ct=ct, cq=cq, dlim=lim.D_limit, snv=snv)
+                            ct=ct, cq=cq, dlim=lim.D_limit, snv=snv, x_rms=getattr(info["_pca"], "x_rms", 0.0))
 
     def transform(self, X):
         """(T2, T2red, Q, Qred) of the LAST model class, as the reference returns (SIMCA.py:101-117)."""

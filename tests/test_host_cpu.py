@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/ocm_simca.h but not exported"
-    assert native.lib().ocm_abi_version() == 1
+    assert native.lib().ocm_abi_version() == 2
     # every bound signature is declared in the header as well
     for s in native.SIGNATURES:
         assert s in syms, f"{s} bound in native.py but not declared in the header"

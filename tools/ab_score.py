@@ -11,7 +11,7 @@ import torch
 
 class ScoreParams(C.Structure):
     _fields_ = [("A", C.c_int32), ("rule", C.c_int32), ("snv", C.c_int32), ("snv_eps", C.c_float),
-                ("ct", C.c_float), ("cq", C.c_float), ("dlim", C.c_float)]
+                ("ct", C.c_float), ("cq", C.c_float), ("dlim", C.c_float), ("x_rms", C.c_float)]      # ABI v2 (older libraries ignore the tail)
 
 
 ap = argparse.ArgumentParser()
@@ -36,12 +36,14 @@ P = Vt[:A].contiguous()
 lam = ((X[:5000] - mu) @ P.T).var(0)
 Sinv = torch.diag(1.0 / lam).contiguous()
 T2 = torch.empty(n, device=dev); Q = torch.empty(n, device=dev); acc = torch.empty(n, dtype=torch.uint8, device=dev)
-hp = ScoreParams(A, 1, a.snv, 1e-8, 0.05, 100.0, 1.4142135)
+x_rms = float(((X[:5000] - mu) ** 2).mean().sqrt())
+hp = ScoreParams(A, 1, a.snv, 1e-8, 0.05, 100.0, 1.4142135, 0.0)
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 ref = None
 for rnd in range(a.rounds):
     for path in a.libs:
-        os.environ['OCM_SCORE_TC1'] = '1' if 'tc1' in os.path.basename(path) else '0'
+        os.environ['OCM_SCORE_TC2'] = '1' if 'tc2' in os.path.basename(path) else '0'
+        hp.x_rms = x_rms if 'f16' in os.path.basename(path) else 0.0
         os.environ['OCM_SCORE_BF16A'] = '1' if 'bf16' in os.path.basename(path) else '0'   # read once per library at its first call
         lib = C.CDLL(os.path.abspath(path))
         fn = lib.ocm_simca_score_tc_f32

@@ -1,2 +1,4 @@
-timeout 300 python -m pytest tests -x -q -m gpu -k "tensor_core or nonfinite" 2>&1 | tail -2
-for lead in 12 13 14; do echo "lead $lead"; OCM_TC2_LEAD=$lead timeout 200 python tools/ab_score.py --libs ab/lib_tc1.so ab/lib_tc2.so --steps 20 --rounds 2 2>&1 | tail -4; done
+timeout 900 python -m pytest tests -x -q -m gpu -k "tensor_core or cluster" 2>&1 | tail -5
+echo "p=2048 tcgen05 cluster-of-four"; timeout 200 python tools/ab_score.py --libs ab/lib_tc1_bf16.so --steps 10 --rounds 1 --p 2048 --rows 5000000 2>&1 | tail -1
+echo "p=2048 row-team"; OCM_DISABLE_TC=1 timeout 200 python tools/step_times.py --steps 10 --rows 5000000 --p 2048 2>&1 | tail -1
+echo "p=2048 dispatcher"; timeout 200 python tools/step_times.py --steps 10 --rows 5000000 --p 2048 2>&1 | tail -1
