@@ -14,8 +14,18 @@ if what in ("score", "all"):
     pca = engine.fit_pca(X[:5000].contiguous(), None, A)
     Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
     for _ in range(3):
-        engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=100.0)
+        engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=100.0, x_rms=pca.x_rms)     # fp16 operand mode + fix-up
+    engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=100.0)                           # bf16 x 3 mode
     torch.cuda.synchronize()
+    if what == "score":
+        # 2048 wavelengths: the cluster kernel, four CTAs per tile
+        X2 = synth.make_spectra_device(1_000_000, 2048, dev, seed=2)
+        pc2 = engine.fit_pca(X2[:5000].contiguous(), None, A)
+        S2 = torch.diag(torch.as_tensor(1.0 / pc2.eigs_all[:A], device=dev))
+        for _ in range(3):
+            engine.score(X2, pc2.mean, pc2.P, S2, rule="alt", ct=0.05, cq=100.0)
+        torch.cuda.synchronize()
+        del X2
     if what == "all":
         # generic kernels: multi-A (CV grid shape), fused SNV, fp64 rows
         Xs = X[:200_000, :1000].contiguous()
