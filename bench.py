@@ -610,7 +610,7 @@ def main():
     total_ms = evs[0].elapsed_time(evs[-1])
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     total_ms_max = odist.max_over_ranks(total_ms, device)
-    kernel_ms = float(np.mean(per_step))           # one launch per step: step time == kernel time
+    kernel_ms = float(np.mean(per_step))           # a step = the scoring kernel (+ its 30 us fp32 fix-up scan in the fp16 mode): charged to the kernel
     accepted = int(out[2].sum().item())
 
     value = world * rows * args.steps / (total_ms_max * 1e-3)
@@ -619,7 +619,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("score_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("score_kernel_dram_bytes_per_launch") if (tj.get("rows") == rows and p == 1024) else None
         except Exception:
             traffic = None
 

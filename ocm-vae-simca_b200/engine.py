@@ -31,7 +31,12 @@ def _p(t):
 
 
 def _stream():
+    """torch's current stream of the current device as the `void* stream` of the C ABI.  The raw getter costs ~1 us;
+    `torch.cuda.current_stream().cuda_stream` builds a Stream object per call (~19 us x ~160 calls in one CV grid)."""
     torch = _torch()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -314,9 +319,9 @@ def covariance(X, row_idx=None, group=None, gram_path="auto", products=None, tim
 def sign_normalise_(V):
     """sklearn svd_flip(u_based_decision=False): the largest-|entry| of each row positive."""
     torch = _torch()
-    idx = V.abs().argmax(dim=1, keepdim=True)
-    sgn = torch.sign(torch.gather(V, 1, idx))
-    sgn[sgn == 0] = 1
+    idx = V.abs().argmax(dim=-1, keepdim=True)           # works on [k, p] and on a batch [F, k, p] alike
+    sgn = torch.sign(torch.gather(V, -1, idx))
+    sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
     V.mul_(sgn)
     return V
 
@@ -472,13 +477,25 @@ def _fold_covariances(X, row_sets):
     one full-size Gram per fold.  Anything else falls back to one covariance per subset."""
     torch = _torch()
     sets_h = [s.cpu().numpy() for s in row_sets]
-    pool = np.unique(np.concatenate(sets_h)) if sets_h else np.zeros(0, np.int64)
-    held = [np.setdiff1d(pool, s, assume_unique=False) for s in sets_h]
-    downdate = len(sets_h) >= 2 and all(len(np.unique(s)) == len(s) for s in sets_h) and \
+    # membership through flag arrays (np.unique / setdiff1d on ten index sets cost 5 ms of a 23 ms grid)
+    n_all = X.shape[0]
+    in_pool = np.zeros(n_all, bool)
+    distinct = True
+    for sh in sets_h:
+        cnt = np.bincount(sh, minlength=n_all) if sh.size else np.zeros(n_all, np.int64)
+        distinct = distinct and (cnt.max(initial=0) <= 1)
+        in_pool |= cnt > 0
+    pool = np.flatnonzero(in_pool)
+    held = []
+    for sh in sets_h:
+        m = in_pool.copy()
+        m[sh] = False
+        held.append(np.flatnonzero(m))
+    downdate = len(sets_h) >= 2 and distinct and \
         all(0 < len(h) < len(s) for h, s in zip(held, sets_h)) and X.shape[0] < GRAM_TC_MIN_ROWS * 4
     if not downdate:
         out = [covariance(X, idx) for idx in row_sets]
-        return [c for c, _, _ in out], [m for _, m, _ in out], [n for _, _, n in out]
+        return [c for c, _, _ in out], [m for _, m, _ in out], [n for _, _, n in out], None
     dev = X.device
     pool_t = index_tensor(pool, dev)
     s0, _, n_pool = colstats(X, pool_t)
@@ -492,7 +509,9 @@ def _fold_covariances(X, row_sets):
         s_h, _, _ = colstats(X, h_t, shift)
         Cm, mean = cov_from_parts(torch.stack([G_pool, G_h]), torch.stack([s_pool, s_h]), [n_pool, len(h)], [1.0, -1.0], shift)
         covs.append(Cm); means.append(mean); ns.append(n_pool - len(h))
-    return covs, means, ns
+    # the pool itself (all rows that are in some training set): a k-fold refit on "everything" is this covariance
+    Cp, mp = cov_from_parts(G_pool.unsqueeze(0), s_pool.unsqueeze(0), [n_pool], [1.0], shift)
+    return covs, means, ns, dict(rows=pool, cov=Cp, mean=mp, n=int(n_pool))
 
 
 def fit_pca_folds(X, row_sets, k) -> list:
@@ -502,20 +521,33 @@ def fit_pca_folds(X, row_sets, k) -> list:
     eigenvalue array."""
     from .limits import Spectrum
     torch = _torch()
-    covs, means, ns = _fold_covariances(X, row_sets)
-    Cs = torch.stack(covs)
+    covs, means, ns, pool = _fold_covariances(X, row_sets)
+    Cs = torch.stack(covs + ([pool["cov"]] if pool is not None else []))      # the pool rides in the same batched solve
     w, V, tails, conv = eig_topk_subspace(Cs, k)
     w_h, tails_h, conv_h = w[:, :k].cpu().numpy(), tails.cpu().numpy(), conv.cpu().numpy()
+    P_all = sign_normalise_(V[:, :, :k].transpose(1, 2).contiguous())      # [F(+1), k, p], one batched pass
     models = []
     for f in range(len(row_sets)):
         if not conv_h[f]:
             models.append(fit_pca(X, row_sets[f], k))
             continue
-        P = V[f, :, :k].transpose(0, 1).contiguous()
-        sign_normalise_(P)
+        P = P_all[f]
         lam = np.maximum(w_h[f], 0.0)
         models.append(PCAModel(mean=means[f], P=P, eigs_all=Spectrum(lam, np.maximum(tails_h[f], 0.0)), n_samples=ns[f]))
+    fit_pca_folds.last_pool = None
+    if pool is not None and conv_h[-1]:
+        from .limits import LazySpectrum
+        f = len(row_sets)
+        P = P_all[f]
+        Cp, n_p, p_ = pool["cov"], pool["n"], X.shape[1]
+        spec = LazySpectrum(np.maximum(w_h[f], 0.0), np.maximum(tails_h[f], 0.0), lambda: _full_spectrum(Cp, n_p, p_))
+        x_rms = float(np.sqrt(max(float(torch.diagonal(Cp).sum()), 0.0) / p_))
+        fit_pca_folds.last_pool = dict(rows=pool["rows"], X=X,
+                                       model=PCAModel(mean=pool["mean"], P=P, eigs_all=spec, n_samples=n_p, x_rms=x_rms))
     return models
+
+
+fit_pca_folds.last_pool = None      # PCA of the union of the row sets of the last call (k components), for a refit on it
 
 
 def eigvals_sym(Cm):

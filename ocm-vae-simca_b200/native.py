@@ -171,8 +171,15 @@ def launch_count():
     return int(lib().ocm_launch_count())
 
 
+_torch_mod = None
+
+
 def require_cuda():
-    import torch
-    if not torch.cuda.is_available():
-        raise NativeError("no CUDA device: the SIMCA hot path has no CPU fallback")
-    return torch
+    """torch, once a CUDA device has been seen (the check is cached: it is on the path of every kernel call)."""
+    global _torch_mod
+    if _torch_mod is None:
+        import torch
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: the SIMCA hot path has no CPU fallback")
+        _torch_mod = torch
+    return _torch_mod

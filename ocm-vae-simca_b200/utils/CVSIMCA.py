@@ -108,6 +108,7 @@ class _FoldModels:
     def __init__(self, Xd, y, splits, cls, A_max, need_train_scores):
         torch = engine._torch()
         self.folds = []
+        self.pool = None
         if not splits:                      # a rank without folds (more ranks than folds)
             return
         row_sets = []
@@ -118,6 +119,7 @@ class _FoldModels:
                 raise ValueError(f"n_components={A_max} too large for a training fold of {int(rows.size)} rows")
             row_sets.append(engine.index_tensor(rows, Xd.device))
         pcas = engine.fit_pca_folds(Xd, row_sets, A_max)       # one batched partial eigensolve for all folds
+        self.pool = engine.fit_pca_folds.last_pool             # PCA of all training rows together (for the refit), or None
         for (tr, te), idx, pca in zip(splits, row_sets, pcas):
             te = np.asarray(te)
             n = int(idx.numel())
@@ -167,19 +169,21 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
         pooled = torch.zeros((n_samples, len(lvs)), dtype=torch.uint8, device=Xd.device)
         writer = torch.zeros((n_samples, len(lvs)), dtype=torch.int32, device=Xd.device) if world > 1 else None
         cnt_folds = torch.zeros((n_folds, len(lvs), 4), dtype=torch.int64, device=Xd.device)
-        for fi, f in zip(mine, fm.folds):
-            # limits of every requested nested model of this fold (host scalars), then ONE launch
-            # scores the fold's test rows and decides for all A at once
-            ct = np.zeros(A_max, np.float32); cq = np.zeros(A_max, np.float32); dl = np.zeros(A_max, np.float32)
+        # limits of every requested nested model of every fold (host scalars), uploaded in ONE copy; then one launch
+        # per fold scores its test rows and decides for all A at once
+        lim_h = np.zeros((max(len(fm.folds), 1), 3, A_max), np.float32)
+        for k_f, f in enumerate(fm.folds):
             for A in lvs:
                 lim = limits.all_limits(prm["type"], prm["t2lim"], prm["t2cl"], prm["qlim"], prm["qcl"], prm["dcl"],
                                         A, f["n"], f["pca"].eigs_all,
                                         f["T2tr"][:, A - 1] if need_train else None,
                                         f["Qtr"][:, A - 1] if need_train else None)
-                ct[A - 1], cq[A - 1] = lim.reduced_scales(prm["type"])
-                dl[A - 1] = lim.D_limit
+                lim_h[k_f, 0, A - 1], lim_h[k_f, 1, A - 1] = lim.reduced_scales(prm["type"])
+                lim_h[k_f, 2, A - 1] = lim.D_limit
+        lim_d = torch.as_tensor(lim_h, device=Xd.device)
+        for k_f, (fi, f) in enumerate(zip(mine, fm.folds)):
             _, _, acc = engine.score_multiA(f["Xte"], f["pca"].mean, f["pca"].P, f["inv_eig"], rule=prm["type"],
-                                            ct=ct, cq=cq, dlim=dl)
+                                            ct=lim_d[k_f, 0], cq=lim_d[k_f, 1], dlim=lim_d[k_f, 2])
             acc = acc.index_select(1, cols).contiguous()
             pooled[f["te_idx"]] = acc
             if writer is not None:
@@ -207,6 +211,7 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
             records.append(rec)
             if store_predictions:
                 by_combo.append({"params": combo.copy(), "LV": rec["LV"], "prediction": pooled_h[:, j].copy()})
+    _run_batched.last_prefit = None if fm.pool is None else dict(X_host=X, Xd=Xd, rows=fm.pool["rows"], model=fm.pool["model"])
     return records, by_combo
 
 
@@ -304,6 +309,10 @@ def cross_validate_simca_grid(estimator, X, y, cv, LV_min=2, LV_max=10, param_gr
     best_estimator.set_params(**best_params)
     if not grid_includes_ncomp:
         best_estimator.set_params(**{_find_ncomp_param_name(best_estimator): best_LV})
+    if use_batched and getattr(_run_batched, "last_prefit", None) is not None:
+        # the batched path has decomposed the pooled training rows already (same batched eigensolve as the folds)
+        best_estimator._prefit = _run_batched.last_prefit
+        _run_batched.last_prefit = None
     best_estimator.fit(X, y)
 
     out = {"results": results_records, "best_params": best_params, "best_LV": best_LV,

@@ -158,16 +158,20 @@ class SIMCA(BaseEstimator, ClassifierMixin):
             print('qlim set as chi2pom')
             self.qlim = 'chi2pom'
 
-        Xd = engine.to_device(X)
+        # CV refit: cross_validate_simca_grid hands over the device copy of X and the decomposition of the pooled
+        # training rows it already has (engine.fit_pca_folds.last_pool); used only for exactly this X and these rows
+        pre = self.__dict__.pop("_prefit", None)
+        Xd = pre["Xd"] if pre is not None and pre["X_host"] is X else engine.to_device(X)
         self._model = {}
         for i, cls in enumerate(self.model_class):
             rows = np.flatnonzero(classes_np == cls)
-            self._model[cls] = self._fit_one_class(Xd, rows, int(self.n_components[i]))
+            self._model[cls] = self._fit_one_class(Xd, rows, int(self.n_components[i]),
+                                                   pre if pre is not None and pre["X_host"] is X else None)
         self.n_features_in_ = Xd.shape[1]
         self.is_fitted_ = True
         return self
 
-    def _fit_one_class(self, Xd, rows, A):
+    def _fit_one_class(self, Xd, rows, A, pre=None):
         """Device restatement of SIMCA.py:62-99.  Small class matrices keep every `_model[cls]` entry eager (scores T
         included); above BULK_FIT_BYTES nothing is copied: the Gram runs through the gather index (or over all rows),
         the training distances come from the bulk scoring kernel and stay on the device, 'perc' / 'chi2pom' limits
@@ -179,7 +183,11 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         n = int(rows.size)
         if not 1 <= A <= min(n - 1, Xd.shape[1], 64):
             raise ValueError(f"n_components={A} must be in 1..min(n_class-1, n_features, 64)")
-        pca = engine.fit_pca(Xd, idx, A)
+        pm = pre["model"] if pre is not None else None
+        if pm is not None and pre["Xd"] is Xd and A <= pm.P.shape[0] and np.array_equal(rows, pre["rows"]):
+            pca = engine.PCAModel(mean=pm.mean, P=pm.P[:A].contiguous(), eigs_all=pm.eigs_all, n_samples=pm.n_samples, x_rms=pm.x_rms)
+        else:
+            pca = engine.fit_pca(Xd, idx, A)
         lam = pca.eigs_all[:A]
         torch = engine._torch()
         inv_eig = torch.as_tensor(1.0 / lam, device=Xd.device)
