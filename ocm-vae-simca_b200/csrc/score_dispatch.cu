@@ -50,13 +50,23 @@ struct HostWorkspace {
         x_bytes = out_rows = model_floats = 0; device = -1;
     }
 };
-HostWorkspace g_ws;
-std::mutex g_ws_mutex;
+// one workspace (and one lock) PER DEVICE: threads that drive different GPUs neither serialise on each other nor tear
+// down each other's staging buffers (round-1 advice); a failing call releases its own device's entry only
+constexpr int kMaxDevices = 64;
+HostWorkspace g_ws[kMaxDevices];
+std::mutex g_ws_mutex[kMaxDevices];
 }  // namespace
 
 extern "C" int ocm_simca_host_release(void) {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    g_ws.release();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        std::lock_guard<std::mutex> lock(g_ws_mutex[d]);
+        if (g_ws[d].device < 0) continue;
+        cudaSetDevice(d);
+        g_ws[d].release();
+    }
+    cudaSetDevice(cur);
     return 0;
 }
 
@@ -72,14 +82,17 @@ extern "C" int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, 
     if (chunk_rows <= 0) chunk_rows = 1 << 16;
     if (chunk_rows > n) chunk_rows = n;
     const int A = hp->A;
-    std::lock_guard<std::mutex> lock(g_ws_mutex);      // one host-buffer call at a time per process
-    HostWorkspace& w = g_ws;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        set_error("ocm_simca_score_host_f32: no usable current device");
+        return (int)cudaErrorInvalidDevice;
+    }
+    std::lock_guard<std::mutex> lock(g_ws_mutex[dev]);      // one host-buffer call at a time per DEVICE
+    HostWorkspace& w = g_ws[dev];
 #define OCM_TRY(call)                                                                        \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                   \
         set_error("%s: %s", #call, cudaGetErrorString(e_)); w.release(); return (int)e_; } } while (0)
-    int dev = 0;
-    OCM_TRY(cudaGetDevice(&dev));
-    if (w.device != dev) { w.release(); w.device = dev; }
+    w.device = dev;
     const size_t need_x = sizeof(float) * (size_t)chunk_rows * p, need_model = (size_t)p + (size_t)A * p + (size_t)A * A;
     for (int b = 0; b < 2; ++b) {
         if (!w.st[b]) OCM_TRY(cudaStreamCreateWithFlags(&w.st[b], cudaStreamNonBlocking));

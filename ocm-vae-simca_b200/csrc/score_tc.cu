@@ -97,7 +97,9 @@ constexpr size_t SM_OFF_S = SM_OFF_MU + P_MAX * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_OFF_MUS = SM_OFF_BAR + 256;                           // -2^XSHIFT * mu (fp16 A-operand mode)
-constexpr size_t SM_TOTAL = SM_OFF_MUS + P_MAX * 4;
+constexpr size_t SM_OFF_ST = SM_OFF_MUS + P_MAX * 4;                      // fused SNV: [4 quarters][128 rows] {mean, M2} of a row's quarter
+constexpr size_t SM_TOTAL = SM_OFF_ST + (size_t)NQ * TILE_M * 8;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
 // fp16 operand mode: every operand is prescaled by a power of two (exact) so that its low-order terms stay clear of the
 // fp16 subnormal range, and the accumulators are scaled back (exactly) when they are read.  The spectra and the scores
 // are scaled from the caller's x_rms (ocm_score_params): y = (x - mu) 2^xs with x_rms 2^xs in (8, 16] (finite up to
@@ -117,6 +119,7 @@ struct Args {
     int inject;               // test hook: CTA 0 drops one TMA stage of its first tile
     uint32_t zero;            // always 0, see mbar_arrive_at_after
     float kx, kt;             // fp16 mode: 2^xs, 2^ts (exact powers of two)
+    float snv_eps;            // fused SNV: x <- (x - mean_row) / (std_row(ddof=0) + snv_eps) before the centring
 };
 
 // mbarrier slots
@@ -130,7 +133,11 @@ static_assert(8 * B_COUNT + 8 <= 256, "barrier block (+ TMEM base word + abort w
 // F16A = fp16 operand mode: the A operand of the projection is a 2-term fp16 split of the prescaled centred spectrum
 // (six converter instructions per pair instead of nine, two TMEM stores and two MMAs per k-step instead of three), the
 // loadings and the scores are 3-term fp16 splits; false = round 1's 3-term bf16 splits everywhere.
-template <bool F16A>
+// SNV = fused standard normal variate (simca_nuts.py:48-50): the tile is streamed a third time, FIRST, for the row mean
+// and standard deviation (each converter thread over its quarter of the columns around its own pivot, the four quarters
+// combined with the parallel-variance formula through shared memory); passes 1 and 2 then read the tile from L2 and fold
+// the normalisation into the centring: xc = x rstd + (-m rstd - mu).
+template <bool F16A, bool SNV>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -252,6 +259,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const uint32_t abase0 = lane_addr + TM_ABUF + (uint32_t)(8 * qd);
         const uint32_t dbase0 = lane_addr + TM_ABUF + (uint32_t)(QCOLS * qd);
 
+        // fused SNV: per-row scale and offset of the normalisation (rstd, -mean rstd), set per tile by the statistics pass
+        f32x2 snv_a = pk2(0u, 0u), snv_ak = pk2(0u, 0u), snv_b = pk2(0u, 0u), snv_bk = pk2(0u, 0u);
+        int first_col = QCOLS * qd;                   // first wavelength of my quarter in the stage being loaded (SNV: padding mask)
         // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
         auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
             mbar_wait(bar_full, ring_phase, wctx);
@@ -259,9 +269,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             for (int i = 0; i < 4; ++i) {
                 const ulonglong2 v = lds128(st + xo[i]);
                 const ulonglong2 m = lds128(mu_addr + 16u * (uint32_t)i);
-                xc[2 * i] = sub2(v.x, m.x);
-                xc[2 * i + 1] = sub2(v.y, m.y);
+                if (SNV) {
+                    // columns beyond p are zero-filled by the TMA: after the normalisation they would not be zero
+                    const bool live = first_col + 4 * i < a.p;
+                    xc[2 * i] = live ? fma2(v.x, snv_a, sub2(snv_b, m.x)) : pk2(0u, 0u);
+                    xc[2 * i + 1] = live ? fma2(v.y, snv_a, sub2(snv_b, m.y)) : pk2(0u, 0u);
+                } else {
+                    xc[2 * i] = sub2(v.x, m.x);
+                    xc[2 * i + 1] = sub2(v.y, m.y);
+                }
             }
+            if (SNV) first_col += STAGE_COLS;
             {
                 uint32_t l0, h0, l1, h1;
                 upk2(xc[5], l0, h0); upk2(xc[7], l1, h1);      // the slot is released only when its loads have returned
@@ -280,8 +298,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             for (int i = 0; i < 4; ++i) {
                 const ulonglong2 v = lds128(st + xo[i]);
                 const ulonglong2 m = lds128(mu_addr + (uint32_t)(SM_OFF_MUS - SM_OFF_MU) + 16u * (uint32_t)i);
-                y[2 * i] = fma2(v.x, k2, m.x);
-                y[2 * i + 1] = fma2(v.y, k2, m.y);
+                if (SNV) {           // y = kx ((x - mean) rstd - mu) = x (kx rstd) + (-kx mean rstd) + (-kx mu); padding stays 0 x P = 0
+                    y[2 * i] = fma2(v.x, snv_ak, add2(snv_bk, m.x));
+                    y[2 * i + 1] = fma2(v.y, snv_ak, add2(snv_bk, m.y));
+                } else {
+                    y[2 * i] = fma2(v.x, k2, m.x);
+                    y[2 * i + 1] = fma2(v.y, k2, m.y);
+                }
             }
             {
                 uint32_t l0, h0, l1, h1;
@@ -292,10 +315,73 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
         };
 
+        float cntq[NQ];                               // fused SNV: wavelengths (not padding) in each column quarter
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int c = 0;
+            if (SNV)
+                for (int j = 0; j < ns; ++j) { const int c0 = STAGE_COLS * j + QCOLS * q; c += c0 >= a.p ? 0 : (a.p - c0 < QCOLS ? a.p - c0 : QCOLS); }
+            cntq[q] = (float)c;
+        }
         for (int64_t k = 0; k < my_tiles; ++k) {
             const uint32_t kpar = (uint32_t)(k & 1);
+            if (SNV) {
+                // ---- pass 0: row statistics.  My quarter of every stage around my own pivot (its first element), so the
+                // sums stay small whatever the baseline of the spectrum; the quarters meet through shared memory.
+                float piv = 0.f, s1 = 0.f, s2 = 0.f;
+                int col = QCOLS * qd;
+#pragma unroll 1
+                for (int sgi = 0; sgi < ns; ++sgi) {
+                    mbar_wait(bar_full, ring_phase, wctx);
+                    float x[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const ulonglong2 v = lds128(st + xo[i]);
+                        uint32_t a0, a1, a2, a3;
+                        upk2(v.x, a0, a1); upk2(v.y, a2, a3);
+                        x[4 * i] = __uint_as_float(a0); x[4 * i + 1] = __uint_as_float(a1);
+                        x[4 * i + 2] = __uint_as_float(a2); x[4 * i + 3] = __uint_as_float(a3);
+                    }
+                    mbar_arrive_at_after<8 * (B_EMPTY - B_FULL)>(bar_full, __float_as_uint(x[11]) | __float_as_uint(x[15]), a.zero);
+                    st += (uint32_t)SM_STAGE; bar_full += 8u;
+                    if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
+                    if (sgi == 0) piv = x[0];                         // column 16 qd < 64 <= p: always a real wavelength
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool live = col + i < a.p;              // columns beyond p are zero padding
+                        const float d = live ? x[i] - piv : 0.f;
+                        s1 += d; s2 = fmaf(d, d, s2);
+                    }
+                    col += STAGE_COLS;
+                }
+                const float nq = cntq[qd];
+                const float mean_q = piv + s1 / nq, m2_q = fmaxf(s2 - s1 * s1 / nq, 0.f);
+                float2* s_st = reinterpret_cast<float2*>(smem + SM_OFF_ST);
+                s_st[qd * TILE_M + row] = make_float2(mean_q, m2_q);
+                named_bar_sync(2, NCONV);
+                float mean = 0.f, m2 = 0.f, ntot = 0.f;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const float2 sq_ = s_st[q * TILE_M + row];
+                    const float nqf = cntq[q];
+                    if (nqf > 0.f) {                                  // Chan's update of (n, mean, M2)
+                        const float delta = sq_.x - mean, nn = ntot + nqf;
+                        mean += delta * nqf / nn;
+                        m2 += sq_.y + delta * delta * ntot * nqf / nn;
+                        ntot = nn;
+                    }
+                }
+                const float rstd = 1.0f / (sqrtf(m2 / ntot) + a.snv_eps);
+                const float b = -mean * rstd;
+                snv_a = pk2(__float_as_uint(rstd), __float_as_uint(rstd));
+                snv_b = pk2(__float_as_uint(b), __float_as_uint(b));
+                snv_ak = pk2(__float_as_uint(rstd * a.kx), __float_as_uint(rstd * a.kx));
+                snv_bk = pk2(__float_as_uint(b * a.kx), __float_as_uint(b * a.kx));
+                named_bar_sync(2, NCONV);                             // the statistics buffer may be rewritten (next tile)
+            }
             // ---- pass 1: centre, split, A operand of the projection (ns is even: stages come in buffer pairs) -------
             uint32_t mu_addr = mu0;
+            first_col = QCOLS * qd;
 #pragma unroll 1
             for (int chunk = 0; chunk < ns; chunk += 2) {
 #pragma unroll
@@ -401,6 +487,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             // accumulate Q = sum r^2 ------------------------------------------------------------------------------
             f32x2 q2 = pk2(0u, 0u);
             mu_addr = mu0;
+            first_col = QCOLS * qd;
 #pragma unroll 1
             for (int c2 = 0; c2 < nc; ++c2) {
                 const uint32_t b = (uint32_t)c2 & 1u;
@@ -470,8 +557,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             bool stop = false;
             for (int64_t k = 0; k < my_tiles && !stop; ++k) {
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
-                for (int w = 0; w < 2 * ns; ++w) {
-                    const int pass = w >= ns ? 1 : 0, chunk = pass ? w - ns : w;
+                constexpr int NPASS = SNV ? 3 : 2;                         // SNV: one more pass, first, for the row statistics
+                for (int w = 0; w < NPASS * ns; ++w) {
+                    const int pass = w / ns == NPASS - 1 ? 1 : 0, chunk = w % ns;   // only the last pass lets the tile go
                     // test hook: the producer of CTA 0 dies before its 4th stage, that stage never arrives
                     if (a.inject && blockIdx.x == 0 && k == 0 && w == 3) { stop = true; break; }
                     mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx);   // all converters drained the slot
@@ -601,7 +689,7 @@ namespace tc {
 __global__ void __launch_bounds__(256) score_fixup_kernel(const float* __restrict__ X, int64_t n, int p, int64_t ldx,
                                                           const float* __restrict__ mu, const float* __restrict__ P,
                                                           const float* __restrict__ Sinv, int A, int rule, float ct, float cq,
-                                                          float dlim, float* T2, float* Q, uint8_t* accept) {
+                                                          float dlim, int snv, float snv_eps, float* T2, float* Q, uint8_t* accept) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -614,11 +702,21 @@ __global__ void __launch_bounds__(256) score_fixup_kernel(const float* __restric
             todo &= todo - 1;
             const int64_t r = base + l;
             const float* x = X + r * ldx;
+            float sa = 1.f, sb = 0.f;                       // fused SNV: x <- x sa + sb (two passes over the row: mean, then variance)
+            if (snv) {
+                float m = 0.f, v = 0.f;
+                for (int j = lane; j < p; j += 32) m += x[j];
+                m = warp_sum(m) / (float)p;
+                for (int j = lane; j < p; j += 32) { const float d = x[j] - m; v = fmaf(d, d, v); }
+                v = warp_sum(v) / (float)p;
+                sa = 1.0f / (sqrtf(v) + snv_eps);
+                sb = -m * sa;
+            }
             float t[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) t[c] = 0.f;
             for (int j = lane; j < p; j += 32) {
-                const float xc = x[j] - mu[j];
+                const float xc = fmaf(x[j], sa, sb) - mu[j];
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     if (c < A) t[c] = fmaf(xc, P[(size_t)c * p + j], t[c]);
@@ -627,7 +725,7 @@ __global__ void __launch_bounds__(256) score_fixup_kernel(const float* __restric
             for (int c = 0; c < 16; ++c) t[c] = warp_sum(t[c]);
             float q = 0.f;
             for (int j = lane; j < p; j += 32) {
-                float rj = x[j] - mu[j];
+                float rj = fmaf(x[j], sa, sb) - mu[j];
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     if (c < A) rj = fmaf(-t[c], P[(size_t)c * p + j], rj);
@@ -666,7 +764,7 @@ extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, i
     static const bool disabled = [] { const char* e = getenv("OCM_DISABLE_TC"); return e && e[0] == '1'; }();
     if (disabled) return 0;
     if (p > ocm::tc::P_MAX) return n >= 32768 ? ocm_simca_score_tc2_supported(n, p, ldx, A, snv, X) : 0;
-    if (snv || p < 64 || p > ocm::tc::P_MAX || (p & 3) || A < 1 || A > ocm::tc::NCOMP) return 0;
+    if (p < 64 || p > ocm::tc::P_MAX || (p & 3) || A < 1 || A > ocm::tc::NCOMP) return 0;      // fused SNV: supported
     if (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
     if (n < 32768 || n >= (1ll << 31) - ocm::tc::TILE_M) return 0;
     return 1;
@@ -682,8 +780,8 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     static const bool use_tc2 = [] { const char* e = getenv("OCM_SCORE_TC2"); return e && e[0] == '1'; }();
     if ((use_tc2 && p <= 1024) || p > tc::P_MAX)        // wider than this kernel's loadings buffer: clusters of four
         return ocm_simca_score_tc2_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, g_inject_polls.exchange(0), stream);
-    OCM_REQUIRE(p >= 64 && p <= tc::P_MAX && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc::NCOMP && !hp->snv, OCM_ELIMIT,
-                "tensor-core path needs 64 <= p <= 1152 (multiple of 4), n_components <= 16, no fused SNV");
+    OCM_REQUIRE(p >= 64 && p <= tc::P_MAX && (p & 3) == 0 && hp->A >= 1 && hp->A <= tc::NCOMP, OCM_ELIMIT,
+                "tensor-core path needs 64 <= p <= 1152 (multiple of 4), n_components <= 16");
     OCM_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0,
                 OCM_EALIGN, "X rows and P must be 16-byte aligned");
     OCM_REQUIRE(n < (1ll << 31) - tc::TILE_M, OCM_ELIMIT, "row count must fit the 32-bit TMA coordinate");
@@ -694,7 +792,7 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     if (rc) return rc;
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f};
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f};
     // fp16 operand mode: only when the caller states the scale of the data (x_rms) and asks for both distances (the
     // fix-up kernel finds out-of-range rows by their non-finite T2 / Q).  OCM_SCORE_BF16A=1 forces the bf16 x 3 mode.
     static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();
@@ -706,7 +804,9 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
         frexpf(hp->x_rms * sqrtf((float)p), &e);
         a.kt = ldexpf(1.0f, 6 - e);                                // |xc| of a typical row times kt in [32, 64)
     }
-    auto kern = f16 ? tc::score_tc_kernel<true> : tc::score_tc_kernel<false>;
+    a.snv_eps = hp->snv_eps;
+    auto kern = f16 ? (hp->snv ? tc::score_tc_kernel<true, true> : tc::score_tc_kernel<true, false>)
+                    : (hp->snv ? tc::score_tc_kernel<false, true> : tc::score_tc_kernel<false, false>);
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
     int64_t blocks = sm_count();
@@ -715,7 +815,7 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     rc = check_launch("score_tc_kernel");
     if (rc || !f16) return rc;
     tc::score_fixup_kernel<<<(unsigned)(2 * sm_count()), 256, 0, (cudaStream_t)stream>>>(X, n, p, ldx, mu, P, Sinv, hp->A, hp->rule, hp->ct,
-                                                                                      hp->cq, hp->dlim, T2, Q, accept);
+                                                                                      hp->cq, hp->dlim, hp->snv, hp->snv_eps, T2, Q, accept);
     return check_launch("score_fixup_kernel");
 }
 

@@ -517,6 +517,35 @@ def test_fused_snv_scoring(torch):
     np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=2e-4)
 
 
+def test_fused_snv_on_the_tensor_core_kernel(torch):
+    """Fused SNV at bulk shapes runs on the tcgen05 kernel (a statistics pass in front of the projection), in both operand
+    modes, padded widths included; against SNV + scoring in fp64 on the SAME fp32 inputs (simca_nuts.py:48-50 feeding
+    utils/SIMCA.py:120-154)."""
+    dev = torch.device("cuda"); lib = native.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr()); st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, A, p in ((40_000, 10, 1024), (33_000, 6, 700), (35_000, 12, 1152), (36_000, 3, 68)):
+        Xraw = synth.make_spectra_device(n, p, dev, seed=p % 53 + A)
+        Xraw = Xraw * (1.0 + 0.3 * torch.rand(n, 1, device=dev)) + 0.5 * torch.rand(n, 1, device=dev)     # row gain and offset: what SNV removes
+        assert lib.ocm_simca_score_tc_supported(n, p, p, A, 1, vp(Xraw)) == 1
+        X64 = Xraw.double()
+        Xs = (X64 - X64.mean(1, keepdim=True)) / (X64.std(1, unbiased=False, keepdim=True) + 1e-8)
+        pca = engine.fit_pca(Xs[:3000].contiguous(), None, A)
+        Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+        model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+        T2r, Qr = so.score(model, Xs.cpu().numpy())
+        mu32, P32 = pca.arrays32(); S32 = Sinv.float().contiguous()
+        for x_rms in (0.0, pca.x_rms):
+            prm = native.ScoreParams(A=A, rule=1, snv=1, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)), x_rms=x_rms)
+            T2 = torch.full((n,), -1.0, device=dev); Q = torch.full((n,), -1.0, device=dev); acc = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+            native.check(lib.ocm_simca_score_f32(vp(Xraw), n, p, p, vp(mu32), vp(P32), vp(S32), C.byref(prm), vp(T2), vp(Q), vp(acc), None, st))
+            assert lib.ocm_simca_score_tc_status() == 0
+            msg = f"n={n} A={A} p={p} x_rms={x_rms}"
+            np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=2e-5, atol=4e-7 * A, err_msg=msg)
+            np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=2e-5, err_msg=msg)
+            d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
+            assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
+
+
 def test_scoring_properties_at_bulk_shape(torch):
     """Size-independent properties at p=1024, A=10 on 300k device-generated rows."""
     dev = torch.device("cuda")
