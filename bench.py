@@ -656,7 +656,7 @@ def main():
         hQ = torch.empty(er, dtype=torch.float32).pin_memory()
         hA = torch.empty(er, dtype=torch.uint8).pin_memory()
         h_mu = mean32.cpu().contiguous(); h_P = P32.cpu().contiguous(); h_S = Sinv.cpu().contiguous()
-        prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=float(ct), cq=float(cq), dlim=float(lim.D_limit))
+        prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=float(ct), cq=float(cq), dlim=float(lim.D_limit), x_rms=float(pca.x_rms))
         vp = lambda t: C.c_void_p(t.data_ptr())
         call = lambda: native.check(native.lib().ocm_simca_score_host_f32(
             vp(hX), er, p, p, vp(h_mu), vp(h_P), vp(h_S), C.byref(prm), 0, vp(hT2), vp(hQ), vp(hA)), "host score")
