@@ -792,7 +792,7 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     if (rc) return rc;
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 20), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f};
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 24), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f};
     // fp16 operand mode: only when the caller states the scale of the data (x_rms) and asks for both distances (the
     // fix-up kernel finds out-of-range rows by their non-finite T2 / Q).  OCM_SCORE_BF16A=1 forces the bf16 x 3 mode.
     static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();

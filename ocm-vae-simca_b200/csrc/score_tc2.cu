@@ -810,7 +810,7 @@ extern "C" int ocm_simca_score_tc2_f32(const float* X, int64_t n, int32_t p, int
     int lead = env_lead > 0 ? env_lead : ns + ns / 2;
     if (lead < ns + 1) lead = ns + 1;                 // pass 2 of a tile needs ALL of its pass 1: anything less deadlocks
     tc2::Args a{n, p, ns, mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-                tc_status_device_ptr(), inject_polls > 0 ? (uint32_t)inject_polls : (1u << 22), inject_polls > 0 ? 1 : 0, lead, env_pol, 0u};
+                tc_status_device_ptr(), inject_polls > 0 ? (uint32_t)inject_polls : (1u << 24), inject_polls > 0 ? 1 : 0, lead, env_pol, 0u};
     return C == 4 ? tc2::launch<4>(tmap, a, (cudaStream_t)stream) : C == 2 ? tc2::launch<2>(tmap, a, (cudaStream_t)stream) : tc2::launch<1>(tmap, a, (cudaStream_t)stream);
 }
 

@@ -534,6 +534,7 @@ def fit_pca_folds(X, row_sets, k) -> list:
         P = P_all[f]
         lam = np.maximum(w_h[f], 0.0)
         models.append(PCAModel(mean=means[f], P=P, eigs_all=Spectrum(lam, np.maximum(tails_h[f], 0.0)), n_samples=ns[f]))
+        models[-1].inv_eig_device = 1.0 / w[f, :k].clamp_min(0.0)      # stays on the device for the multi-A scoring launch
     fit_pca_folds.last_pool = None
     if pool is not None and conv_h[-1]:
         from .limits import LazySpectrum

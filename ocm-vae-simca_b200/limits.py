@@ -58,6 +58,15 @@ class Spectrum:
     def __init__(self, top, tail):
         self.top = np.asarray(top, dtype=np.float64)
         self.tail = tuple(float(t) for t in tail)       # (sum, sum of squares, sum of cubes) of lambda_{k+1..}
+        self._sfx = None
+
+    def suffix_sums(self):
+        """sfx[i][A] = sum_{k >= A} top[k]^(i+1), A = 0..len(top): the tail moments of every nested model in O(1)
+        (the CV grid asks for all A of every fold)."""
+        if self._sfx is None:
+            z = np.zeros(1)
+            self._sfx = tuple(np.concatenate([np.cumsum((self.top ** k)[::-1])[::-1], z]) for k in (1, 2, 3))
+        return self._sfx
 
     def __getitem__(self, sl):
         return self.top[sl]
@@ -91,9 +100,9 @@ def tail_moments(eigs_all, A):
     if isinstance(eigs_all, Spectrum):
         if A > len(eigs_all.top):
             raise ValueError("partial spectrum shorter than n_components")
-        rest = eigs_all.top[A:]
+        s1, s2, s3 = eigs_all.suffix_sums()
         t1, t2, t3 = eigs_all.tail
-        return float(t1 + rest.sum()), float(t2 + (rest ** 2).sum()), float(t3 + (rest ** 3).sum())
+        return float(t1 + s1[A]), float(t2 + s2[A]), float(t3 + s3[A])
     tail = np.asarray(eigs_all, dtype=np.float64)[A:]
     return float(tail.sum()), float((tail ** 2).sum()), float((tail ** 3).sum())
 

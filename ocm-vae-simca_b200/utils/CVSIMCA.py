@@ -120,13 +120,20 @@ class _FoldModels:
             row_sets.append(engine.index_tensor(rows, Xd.device))
         pcas = engine.fit_pca_folds(Xd, row_sets, A_max)       # one batched partial eigensolve for all folds
         self.pool = engine.fit_pca_folds.last_pool             # PCA of all training rows together (for the refit), or None
-        for (tr, te), idx, pca in zip(splits, row_sets, pcas):
-            te = np.asarray(te)
+        # test rows and target flags of all folds in ONE upload each
+        tes = [np.asarray(te) for _, te in splits]
+        offs = np.concatenate([[0], np.cumsum([t.size for t in tes])])
+        te_all = engine.index_tensor(np.concatenate(tes) if tes else np.zeros(0, np.int64), Xd.device)
+        tgt_all = torch.as_tensor((y[np.concatenate(tes)] == cls).astype(np.uint8) if tes else np.zeros(0, np.uint8), device=Xd.device)
+        for k_f, ((tr, te), idx, pca) in enumerate(zip(splits, row_sets, pcas)):
+            te = tes[k_f]
             n = int(idx.numel())
-            inv_eig = torch.as_tensor(1.0 / pca.eigs_all[:A_max], device=Xd.device)
-            te_idx = engine.index_tensor(te, Xd.device)
+            inv_eig = getattr(pca, "inv_eig_device", None)
+            if inv_eig is None:
+                inv_eig = torch.as_tensor(1.0 / pca.eigs_all[:A_max], device=Xd.device)
+            te_idx = te_all[int(offs[k_f]):int(offs[k_f + 1])]
             f = dict(pca=pca, n=n, te=te, te_idx=te_idx, Xte=Xd.index_select(0, te_idx), inv_eig=inv_eig,
-                     is_target=torch.as_tensor((y[te] == cls).astype(np.uint8), device=Xd.device))
+                     is_target=tgt_all[int(offs[k_f]):int(offs[k_f + 1])])
             if need_train_scores:
                 T2tr, Qtr, _ = engine.score_multiA(Xd.index_select(0, idx), pca.mean, pca.P, inv_eig)
                 f["T2tr"] = T2tr.double().cpu().numpy()
