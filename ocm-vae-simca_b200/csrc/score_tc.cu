@@ -558,8 +558,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
             for (int64_t k = 0; k < my_tiles && !stop; ++k) {
                 const int row0 = (int)(((int64_t)blockIdx.x + k * gridDim.x) * TILE_M);
                 constexpr int NPASS = SNV ? 3 : 2;                         // SNV: one more pass, first, for the row statistics
-                for (int w = 0; w < NPASS * ns; ++w) {
-                    const int pass = w / ns == NPASS - 1 ? 1 : 0, chunk = w % ns;   // only the last pass lets the tile go
+                const int nw = NPASS * ns, last0 = (NPASS - 1) * ns;
+                // (no division here: an integer divide per stage on this lane's critical path -- it re-arms a ring of three
+                // slots -- cost the whole kernel 3-5 %, A/B-measured)
+                for (int w = 0, chunk = 0; w < nw; ++w, ++chunk) {
+                    if (chunk == ns) chunk = 0;
+                    const int pass = w >= last0 ? 1 : 0;                   // only the last pass lets the tile go
                     // test hook: the producer of CTA 0 dies before its 4th stage, that stage never arrives
                     if (a.inject && blockIdx.x == 0 && k == 0 && w == 3) { stop = true; break; }
                     mbar_wait(BAR(B_EMPTY + slot), ring_phase ^ 1, wctx);   // all converters drained the slot
