@@ -97,8 +97,8 @@ constexpr size_t SM_OFF_S = SM_OFF_MU + P_MAX * 4;
 constexpr size_t SM_OFF_Q = SM_OFF_S + NCOMP * NCOMP * 4;
 constexpr size_t SM_OFF_BAR = SM_OFF_Q + (size_t)NQ * TILE_M * 4;
 constexpr size_t SM_OFF_MUS = SM_OFF_BAR + 256;                           // -2^XSHIFT * mu (fp16 A-operand mode)
-constexpr size_t SM_OFF_ST = SM_OFF_MUS + P_MAX * 4;                      // fused SNV: [4 quarters][128 rows] {mean, M2} of a row's quarter
-constexpr size_t SM_TOTAL = SM_OFF_ST + (size_t)NQ * TILE_M * 8;
+constexpr size_t SM_OFF_ST = SM_OFF_MUS + P_MAX * 4;                      // fused SNV: [4 quarters][128 rows] {pivot, mean - pivot, M2, -} of a row's quarter
+constexpr size_t SM_TOTAL = SM_OFF_ST + (size_t)NQ * TILE_M * 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 // fp16 operand mode: every operand is prescaled by a power of two (exact) so that its low-order terms stay clear of the
 // fp16 subnormal range, and the accumulators are scaled back (exactly) when they are read.  The spectra and the scores
@@ -260,7 +260,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
         const uint32_t dbase0 = lane_addr + TM_ABUF + (uint32_t)(QCOLS * qd);
 
         // fused SNV: per-row scale and offset of the normalisation (rstd, -mean rstd), set per tile by the statistics pass
-        f32x2 snv_a = pk2(0u, 0u), snv_ak = pk2(0u, 0u), snv_b = pk2(0u, 0u), snv_bk = pk2(0u, 0u);
+        // xc = (x - ref) rstd + (-(mean - ref) rstd - mu): the mean is carried as an exact fp32 reference value plus a small
+        // correction, so that neither it nor the offset it turns into is rounded at the size of the spectrum's baseline
+        f32x2 snv_a = pk2(0u, 0u), snv_ak = pk2(0u, 0u), snv_b = pk2(0u, 0u), snv_bk = pk2(0u, 0u), snv_ref = pk2(0u, 0u);
         int first_col = QCOLS * qd;                   // first wavelength of my quarter in the stage being loaded (SNV: padding mask)
         // one stage: wait for the TMA, my 16 columns -> registers (centred), release the slot
         auto load_stage = [&](uint32_t mu_addr, f32x2* xc) {
@@ -272,8 +274,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 if (SNV) {
                     // columns beyond p are zero-filled by the TMA: after the normalisation they would not be zero
                     const bool live = first_col + 4 * i < a.p;
-                    xc[2 * i] = live ? fma2(v.x, snv_a, sub2(snv_b, m.x)) : pk2(0u, 0u);
-                    xc[2 * i + 1] = live ? fma2(v.y, snv_a, sub2(snv_b, m.y)) : pk2(0u, 0u);
+                    xc[2 * i] = live ? fma2(sub2(v.x, snv_ref), snv_a, sub2(snv_b, m.x)) : pk2(0u, 0u);
+                    xc[2 * i + 1] = live ? fma2(sub2(v.y, snv_ref), snv_a, sub2(snv_b, m.y)) : pk2(0u, 0u);
                 } else {
                     xc[2 * i] = sub2(v.x, m.x);
                     xc[2 * i + 1] = sub2(v.y, m.y);
@@ -299,8 +301,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                 const ulonglong2 v = lds128(st + xo[i]);
                 const ulonglong2 m = lds128(mu_addr + (uint32_t)(SM_OFF_MUS - SM_OFF_MU) + 16u * (uint32_t)i);
                 if (SNV) {           // y = kx ((x - mean) rstd - mu) = x (kx rstd) + (-kx mean rstd) + (-kx mu); padding stays 0 x P = 0
-                    y[2 * i] = fma2(v.x, snv_ak, add2(snv_bk, m.x));
-                    y[2 * i + 1] = fma2(v.y, snv_ak, add2(snv_bk, m.y));
+                    y[2 * i] = fma2(sub2(v.x, snv_ref), snv_ak, add2(snv_bk, m.x));
+                    y[2 * i + 1] = fma2(sub2(v.y, snv_ref), snv_ak, add2(snv_bk, m.y));
                 } else {
                     y[2 * i] = fma2(v.x, k2, m.x);
                     y[2 * i + 1] = fma2(v.y, k2, m.y);
@@ -346,33 +348,40 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     st += (uint32_t)SM_STAGE; bar_full += 8u;
                     if (bar_full == bar_full_end) { st = ring0; bar_full = bar_full0; ring_phase ^= 1u; }
                     if (sgi == 0) piv = x[0];                         // column 16 qd < 64 <= p: always a real wavelength
+                    // per-stage partial sums in four lanes, then one addition into the running totals: 256 sequential fp32
+                    // additions lost 1e-6 of the variance, which T2 (a ratio to small eigenvalues) shows at 2e-5
+                    float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const bool live = col + i < a.p;              // columns beyond p are zero padding
                         const float d = live ? x[i] - piv : 0.f;
-                        s1 += d; s2 = fmaf(d, d, s2);
+                        p1[i & 3] += d; p2[i & 3] = fmaf(d, d, p2[i & 3]);
                     }
+                    s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                    s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
                     col += STAGE_COLS;
                 }
                 const float nq = cntq[qd];
-                const float mean_q = piv + s1 / nq, m2_q = fmaxf(s2 - s1 * s1 / nq, 0.f);
-                float2* s_st = reinterpret_cast<float2*>(smem + SM_OFF_ST);
-                s_st[qd * TILE_M + row] = make_float2(mean_q, m2_q);
+                const float c_q = s1 / nq, m2_q = fmaxf(s2 - s1 * c_q, 0.f);
+                float4* s_st = reinterpret_cast<float4*>(smem + SM_OFF_ST);
+                s_st[qd * TILE_M + row] = make_float4(piv, c_q, m2_q, 0.f);
                 named_bar_sync(2, NCONV);
-                float mean = 0.f, m2 = 0.f, ntot = 0.f;
+                const float ref = s_st[row].x;                        // quarter 0's pivot: every quarter of the row agrees on it
+                float mrel = 0.f, m2 = 0.f, ntot = 0.f;               // mean relative to ref
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    const float2 sq_ = s_st[q * TILE_M + row];
+                    const float4 sq_ = s_st[q * TILE_M + row];
                     const float nqf = cntq[q];
                     if (nqf > 0.f) {                                  // Chan's update of (n, mean, M2)
-                        const float delta = sq_.x - mean, nn = ntot + nqf;
-                        mean += delta * nqf / nn;
-                        m2 += sq_.y + delta * delta * ntot * nqf / nn;
+                        const float delta = ((sq_.x - ref) + sq_.y) - mrel, nn = ntot + nqf;
+                        mrel += delta * nqf / nn;
+                        m2 += sq_.z + delta * delta * ntot * nqf / nn;
                         ntot = nn;
                     }
                 }
                 const float rstd = 1.0f / (sqrtf(m2 / ntot) + a.snv_eps);
-                const float b = -mean * rstd;
+                const float b = -mrel * rstd;
+                snv_ref = pk2(__float_as_uint(ref), __float_as_uint(ref));
                 snv_a = pk2(__float_as_uint(rstd), __float_as_uint(rstd));
                 snv_b = pk2(__float_as_uint(b), __float_as_uint(b));
                 snv_ak = pk2(__float_as_uint(rstd * a.kx), __float_as_uint(rstd * a.kx));

@@ -525,7 +525,8 @@ def test_fused_snv_on_the_tensor_core_kernel(torch):
     vp = lambda t: C.c_void_p(t.data_ptr()); st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     for n, A, p in ((40_000, 10, 1024), (33_000, 6, 700), (35_000, 12, 1152), (36_000, 3, 68)):
         Xraw = synth.make_spectra_device(n, p, dev, seed=p % 53 + A)
-        Xraw = Xraw * (1.0 + 0.3 * torch.rand(n, 1, device=dev)) + 0.5 * torch.rand(n, 1, device=dev)     # row gain and offset: what SNV removes
+        g = torch.Generator(device=dev); g.manual_seed(1000 + p)
+        Xraw = Xraw * (1.0 + 0.3 * torch.rand(n, 1, device=dev, generator=g)) + 0.5 * torch.rand(n, 1, device=dev, generator=g)     # row gain and offset: what SNV removes
         assert lib.ocm_simca_score_tc_supported(n, p, p, A, 1, vp(Xraw)) == 1
         X64 = Xraw.double()
         Xs = (X64 - X64.mean(1, keepdim=True)) / (X64.std(1, unbiased=False, keepdim=True) + 1e-8)
@@ -540,8 +541,8 @@ def test_fused_snv_on_the_tensor_core_kernel(torch):
             native.check(lib.ocm_simca_score_f32(vp(Xraw), n, p, p, vp(mu32), vp(P32), vp(S32), C.byref(prm), vp(T2), vp(Q), vp(acc), None, st))
             assert lib.ocm_simca_score_tc_status() == 0
             msg = f"n={n} A={A} p={p} x_rms={x_rms}"
-            np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=2e-5, atol=4e-7 * A, err_msg=msg)
-            np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=2e-5, err_msg=msg)
+            np.testing.assert_allclose(T2.cpu().numpy(), T2r, rtol=1.5e-5, atol=4e-7 * A, err_msg=msg)      # measured: <= 9e-6
+            np.testing.assert_allclose(Q.cpu().numpy(), Qr, rtol=1.5e-5, err_msg=msg)
             d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
             assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
 
