@@ -120,6 +120,7 @@ struct Args {
     uint32_t zero;            // always 0, see mbar_arrive_at_after
     float kx, kt;             // fp16 mode: 2^xs, 2^ts (exact powers of two)
     float snv_eps;            // fused SNV: x <- (x - mean_row) / (std_row(ddof=0) + snv_eps) before the centring
+    int map3d;                // the tensor map has a third dimension (32-column blocks): one TMA instruction per stage
 };
 
 // mbarrier slots
@@ -579,8 +580,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     mbar_expect_tx(BAR(B_FULL + slot), (uint32_t)SM_STAGE);
                     const uint32_t dst = sb + (uint32_t)SM_OFF_RING + (uint32_t)slot * (uint32_t)SM_STAGE;
                     const uint64_t pol = pass == 0 ? pol_keep : pol_stream;
-                    tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
-                    tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
+                    if (a.map3d) {       // both 32-column boxes of the stage with one instruction
+                        tma_load_3d(dst, &tmap, 0, row0, 2 * chunk, BAR(B_FULL + slot), pol);
+                    } else {
+                        tma_load_2d(dst, &tmap, chunk * STAGE_COLS, row0, BAR(B_FULL + slot), pol);
+                        tma_load_2d(dst + (uint32_t)SM_BOX, &tmap, chunk * STAGE_COLS + BOX_COLS, row0, BAR(B_FULL + slot), pol);
+                    }
                     if (++slot == NSTAGE) { slot = 0; ring_phase ^= 1; }
                 }
             }
@@ -664,7 +669,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, int64_t ldx) {
+static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, int64_t ldx, bool three_d) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -676,13 +681,27 @@ static int make_tensor_map(CUtensorMap* map, const float* X, int64_t n, int p, i
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)p, (cuuint64_t)n};      // columns >= p of a box are zero filled
-    const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)BOX_COLS, (cuuint32_t)TILE_M};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (three_d) {
+        // (32 columns, rows, 32-column blocks): a box of {32, 128, 2} is a whole 64-column stage, laid out in shared memory
+        // as the two swizzled 128 x 32 boxes the converters expect.  Only for p % 32 == 0 (a partial block would not be
+        // zero filled but read on into the next row).
+        const cuuint64_t dims[3] = {(cuuint64_t)BOX_COLS, (cuuint64_t)n, (cuuint64_t)(p / BOX_COLS)};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldx * sizeof(float), (cuuint64_t)BOX_COLS * sizeof(float)};
+        const cuuint32_t box[3] = {(cuuint32_t)BOX_COLS, (cuuint32_t)TILE_M, 2};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[2] = {(cuuint64_t)p, (cuuint64_t)n};      // columns >= p of a box are zero filled
+        const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)BOX_COLS, (cuuint32_t)TILE_M};
+        const cuuint32_t estr[2] = {1, 1};
+        r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return (int)cudaErrorInvalidValue;
@@ -801,11 +820,13 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     int rc = tc_status_report("ocm_simca_score_tc_f32");          // an EARLIER launch trapped: say so before touching the driver
     if (rc) return rc;
     CUtensorMap tmap;
-    rc = tc::make_tensor_map(&tmap, X, n, p, ldx);
+    static const bool map2d_only = [] { const char* e = getenv("OCM_SCORE_TMA2D"); return e && e[0] == '1'; }();      // A/B switch
+    const bool map3d = !map2d_only && p % tc::BOX_COLS == 0;
+    rc = tc::make_tensor_map(&tmap, X, n, p, ldx, map3d);
     if (rc) return rc;
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 24), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f};
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 24), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f, map3d ? 1 : 0};
     // fp16 operand mode: only when the caller states the scale of the data (x_rms) and asks for both distances (the
     // fix-up kernel finds out-of-range rows by their non-finite T2 / Q).  OCM_SCORE_BF16A=1 forces the bf16 x 3 mode.
     static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();

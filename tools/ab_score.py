@@ -42,6 +42,7 @@ stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 ref = None
 for rnd in range(a.rounds):
     for path in a.libs[rnd % len(a.libs):] + a.libs[:rnd % len(a.libs)]:      # rotate: the first of a round meets the coolest GPU
+        os.environ['OCM_SCORE_TMA2D'] = '1' if 'tma2d' in os.path.basename(path) else '0'
         os.environ['OCM_SCORE_TC2'] = '1' if 'tc2' in os.path.basename(path) else '0'
         hp.x_rms = x_rms if 'f16' in os.path.basename(path) else 0.0
         os.environ['OCM_SCORE_BF16A'] = '1' if 'bf16' in os.path.basename(path) else '0'   # read once per library at its first call
