@@ -832,6 +832,29 @@ def test_host_buffer_api(torch):
     assert lib.ocm_simca_host_release() == 0 and lib.ocm_simca_host_release() == 0
 
 
+def test_host_buffer_api_bulk_chunks_take_the_tensor_core_kernel(torch):
+    """Host buffers with chunks large enough for the tcgen05 kernel, in its fp16 operand mode (x_rms given): every chunk
+    is followed by its own fix-up scan; a row 1e6 times out of range must come back finite and rejected."""
+    n, p, A = 100_000, 1024, 10
+    X = synth.make_spectra(n, p, seed=21).astype(np.float32)
+    X[70_001] *= 1e6
+    ref = so.fit_one_class(X[:3000].astype(np.float64), A)
+    T2r, Qr = so.score(ref, X.astype(np.float64))
+    mu = ref["pred_mean"].astype(np.float32); P = np.ascontiguousarray(ref["pred_P"], np.float32)
+    S = np.ascontiguousarray(ref["Sinv"], np.float32)
+    x_rms = float(np.sqrt(np.sum(ref["eigs_all"]) / p))
+    prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=1.0 / ref["T2_limit"], cq=1.0 / ref["Q_limit"],
+                             dlim=float(ref["D_limit"]), x_rms=x_rms)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    T2 = np.empty(n, np.float32); Q = np.empty(n, np.float32); acc = np.empty(n, np.uint8)
+    native.check(native.lib().ocm_simca_score_host_f32(vp(X), n, p, p, vp(mu), vp(P), vp(S), C.byref(prm), 40_000, vp(T2), vp(Q), vp(acc)))
+    assert native.lib().ocm_simca_score_tc_supported(40_000, p, p, A, 0, None) == 1
+    np.testing.assert_allclose(T2, T2r, rtol=RTOL, atol=2e-7 * A)
+    np.testing.assert_allclose(Q, Qr, rtol=RTOL)
+    assert np.isfinite(T2[70_001]) and acc[70_001] == 0
+    assert_decisions(acc.astype(float), so.predict(ref, X.astype(np.float64)), so.reduced_distance(ref, T2r, Qr), ref["D_limit"])
+
+
 def test_cv_grid_folds_over_ranks(torch):
     """§8(e): folds dealt over two ranks (gloo, both on this GPU) give the single-process CV table on every rank."""
     import subprocess, sys, json
