@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int  sm_count();
 unsigned int* tc_status_device_ptr();      // device-visible status word of the tcgen05 kernels (mapped host memory)
+unsigned int* tc_flag_device_ptr();        // device word of the fp16-mode fix-up (see runtime.cu); NULL if it cannot be had
 int  tc_status_take();                     // read from the host (no device access); 0 = clean
 int  tc_status_report(const char* where);  // 0, or OCM_ETIMEOUT with the error text set
 

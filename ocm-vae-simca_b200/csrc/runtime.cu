@@ -60,6 +60,24 @@ unsigned int* tc_status_device_ptr() {
     return w.dev;
 }
 
+// One 32-bit word per device in DEVICE memory for the fp16 operand mode of the scoring kernel: a launch that produced a
+// non-finite distance stores its launch id there (atomicMax), and the fix-up kernel that follows on the same stream
+// scans T2 / Q only when it finds its own id -- otherwise every CTA reads one word and leaves.  Never reset (ids grow).
+namespace {
+unsigned int* g_flag[64];
+}
+unsigned int* tc_flag_device_ptr() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_flag[dev]) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, 64) != cudaSuccess) return nullptr;
+        if (cudaMemset(d, 0, 64) != cudaSuccess) { cudaFree(d); return nullptr; }
+        g_flag[dev] = static_cast<unsigned int*>(d);
+    }
+    return g_flag[dev];
+}
+
 int tc_status_take() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;

@@ -121,6 +121,8 @@ struct Args {
     float kx, kt;             // fp16 mode: 2^xs, 2^ts (exact powers of two)
     float snv_eps;            // fused SNV: x <- (x - mean_row) / (std_row(ddof=0) + snv_eps) before the centring
     int map3d;                // the tensor map has a third dimension (32-column blocks): one TMA instruction per stage
+    unsigned int* nf_flag;    // fp16 mode: receives nf_id when a row comes out non-finite (the fix-up kernel then scans)
+    unsigned int nf_id;
 };
 
 // mbarrier slots
@@ -548,6 +550,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap, Args a) {
                     const float tt = t2_row;
                     if (a.T2) a.T2[grow] = tt;
                     if (a.Q) a.Q[grow] = qq;
+                    if (F16A && a.nf_flag && !(isfinite(tt) && isfinite(qq))) atomicMax(a.nf_flag, a.nf_id);
                     if (a.accept) a.accept[grow] = rule_distance(a.rule, tt * a.ct, qq * a.cq) < a.dlim ? 1 : 0;
                 }
             }
@@ -721,7 +724,10 @@ namespace tc {
 __global__ void __launch_bounds__(256) score_fixup_kernel(const float* __restrict__ X, int64_t n, int p, int64_t ldx,
                                                           const float* __restrict__ mu, const float* __restrict__ P,
                                                           const float* __restrict__ Sinv, int A, int rule, float ct, float cq,
-                                                          float dlim, int snv, float snv_eps, float* T2, float* Q, uint8_t* accept) {
+                                                          float dlim, int snv, float snv_eps, float* T2, float* Q, uint8_t* accept,
+                                                          const unsigned int* nf_flag, unsigned int nf_id) {
+    // my launch (or a later one on another stream: atomicMax) has stored an id >= mine if it saw such a row; an earlier flag is < mine
+    if (nf_flag && *reinterpret_cast<const volatile unsigned int*>(nf_flag) < nf_id) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -826,7 +832,7 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     if (rc) return rc;
     const int inject = g_inject_polls.exchange(0);
     tc::Args a{n, p, 2 * ((p + tc::D2_COLS - 1) / tc::D2_COLS), mu, P, Sinv, hp->A, hp->rule, hp->ct, hp->cq, hp->dlim, T2, Q, accept,
-               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 24), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f, map3d ? 1 : 0};
+               tc_status_device_ptr(), inject > 0 ? (uint32_t)inject : (1u << 24), inject > 0 ? 1 : 0, 0u, 1.0f, 1.0f, 1e-8f, map3d ? 1 : 0, nullptr, 0u};
     // fp16 operand mode: only when the caller states the scale of the data (x_rms) and asks for both distances (the
     // fix-up kernel finds out-of-range rows by their non-finite T2 / Q).  OCM_SCORE_BF16A=1 forces the bf16 x 3 mode.
     static const bool bf16a = [] { const char* e = getenv("OCM_SCORE_BF16A"); return e && e[0] == '1'; }();
@@ -839,6 +845,9 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
         a.kt = ldexpf(1.0f, 6 - e);                                // |xc| of a typical row times kt in [32, 64)
     }
     a.snv_eps = hp->snv_eps;
+    static std::atomic<unsigned int> launch_id{0};
+    a.nf_flag = f16 ? tc_flag_device_ptr() : nullptr;          // NULL (allocation failed): the fix-up scans unconditionally
+    a.nf_id = launch_id.fetch_add(1) + 1;
     auto kern = f16 ? (hp->snv ? tc::score_tc_kernel<true, true> : tc::score_tc_kernel<true, false>)
                     : (hp->snv ? tc::score_tc_kernel<false, true> : tc::score_tc_kernel<false, false>);
     OCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SM_TOTAL));
@@ -849,7 +858,7 @@ extern "C" int ocm_simca_score_tc_f32(const float* X, int64_t n, int32_t p, int6
     rc = check_launch("score_tc_kernel");
     if (rc || !f16) return rc;
     tc::score_fixup_kernel<<<(unsigned)(2 * sm_count()), 256, 0, (cudaStream_t)stream>>>(X, n, p, ldx, mu, P, Sinv, hp->A, hp->rule, hp->ct,
-                                                                                      hp->cq, hp->dlim, hp->snv, hp->snv_eps, T2, Q, accept);
+                                                                                      hp->cq, hp->dlim, hp->snv, hp->snv_eps, T2, Q, accept, a.nf_flag, a.nf_id);
     return check_launch("score_fixup_kernel");
 }
 
