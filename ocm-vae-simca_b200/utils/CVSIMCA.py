@@ -29,54 +29,75 @@ _LIMIT_PARAMS = {"type", "t2lim", "t2cl", "qlim", "qcl", "dcl", "verbose", "maxP
 
 
 class ClasswiseKFoldWithExternalVal(BaseCrossValidator):
-    """K-fold over the TARGET class only; every test fold = held-out target rows + ALL rows of
-    the other classes (CVSIMCA.py:39-80).  Give either `cls_idx` (row indices of the target
-    class) or `cls_label` (resolved against y inside split)."""
+    """One-class cross-validation splitter with the reference's protocol (CVSIMCA.py:39-80): only the rows of the TARGET
+    class are divided into `n_splits` folds; a training set is the target rows outside the fold, a test set is the fold
+    plus EVERY row of the other classes (so the other classes are tested in each split).  The target rows are given
+    either as row indices (`cls_idx`) or as a label to look up in `y` (`cls_label`; a scalar `cls_idx` is read as a label
+    too)."""
 
     def __init__(self, n_splits=5, cls_idx=None, cls_label=None, shuffle=False, random_state=None):
-        self.kf = KFold(n_splits=n_splits, shuffle=shuffle, random_state=random_state)
-        self.cls_idx = None if cls_idx is None else np.asarray(cls_idx)
+        self.kf = KFold(n_splits=n_splits, shuffle=shuffle, random_state=random_state)     # attribute kept: callers read it
+        self.cls_idx = cls_idx if cls_idx is None else np.asarray(cls_idx)
         self.cls_label = cls_label
 
     def get_n_splits(self, X=None, y=None, groups=None):
         return self.kf.get_n_splits()
 
-    def split(self, X, y=None, groups=None):
-        if y is None and self.cls_idx is None and self.cls_label is not None:
-            raise ValueError("cls_label needs y in split(X, y).")
-        target = self.cls_idx
-        if target is None and self.cls_label is not None:
-            target = np.flatnonzero(y == self.cls_label)
-        if target is not None and np.ndim(target) == 0:      # a label passed as cls_idx by mistake
-            if y is None:
-                raise ValueError("cls_idx is a scalar; y is needed to resolve it to row indices.")
-            target = np.flatnonzero(y == int(target))
-        if target is None or target.size == 0:
+    def _target_rows(self, y):
+        """Row indices of the target class, validated against the number of folds."""
+        label = None
+        if self.cls_idx is not None and self.cls_idx.ndim > 0:
+            rows = self.cls_idx
+        else:
+            label = self.cls_label if self.cls_idx is None else int(self.cls_idx)
+            if label is None:
+                rows = np.zeros(0, dtype=np.int64)
+            elif y is None:
+                raise ValueError("the target class is given as a label: split(X, y) needs y to find its rows.")
+            else:
+                rows = np.flatnonzero(np.asarray(y) == label)
+        if rows.size == 0:
             raise ValueError("cls_idx is empty: no sample of the target class found.")
-        if target.size < self.kf.n_splits:
-            raise ValueError(f"Too many splits ({self.kf.n_splits}) for {target.size} target-class samples.")
-        others = np.setdiff1d(np.arange(X.shape[0]), target)
-        for tr, te in self.kf.split(target):
-            yield target[tr], np.concatenate([target[te], others])
+        if rows.size < self.kf.n_splits:
+            raise ValueError(f"Too many splits ({self.kf.n_splits}) for {rows.size} target-class samples.")
+        return rows
+
+    def split(self, X, y=None, groups=None):
+        rows = self._target_rows(y)
+        outside = np.ones(X.shape[0], dtype=bool)
+        outside[rows] = False
+        others = np.flatnonzero(outside)                      # sorted, like the reference's setdiff1d
+        for keep, held in self.kf.split(rows):
+            yield rows[keep], np.concatenate((rows[held], others))
+
+
+def _simca_steps(estimator):
+    """[(parameter prefix, object)] of everything in `estimator` that speaks the SIMCA metric protocol
+    (`_metrics_simca_conformity`, CVSIMCA.py:85-98): the estimator itself, or the matching steps of a Pipeline in order."""
+    speaks = lambda obj: hasattr(obj, "_metrics_simca_conformity")
+    if speaks(estimator):
+        return [("", estimator)]
+    if isinstance(estimator, Pipeline):
+        return [(name + "__", step) for name, step in estimator.named_steps.items() if speaks(step)]
+    return []
 
 
 def _get_simca(estimator):
-    if hasattr(estimator, "_metrics_simca_conformity"):
-        return estimator
-    if isinstance(estimator, Pipeline):
-        for _, step in reversed(list(estimator.named_steps.items())):
-            if hasattr(step, "_metrics_simca_conformity"):
-                return step
-    raise AttributeError("no SIMCA object found in the estimator.")
+    """The SIMCA object inside `estimator` (the LAST matching step of a Pipeline)."""
+    found = _simca_steps(estimator)
+    if not found:
+        raise AttributeError("no SIMCA object found in the estimator.")
+    return found[-1][1]
 
 
 def _find_ncomp_param_name(estimator):
-    if isinstance(estimator, Pipeline):
-        for name, step in estimator.named_steps.items():
-            if hasattr(step, "_metrics_simca_conformity"):
-                return f"{name}__n_components"
+    """Parameter path of n_components: '<step>__n_components' for the first SIMCA step of a Pipeline, else 'n_components'."""
+    if not isinstance(estimator, Pipeline):
+        return "n_components"
+    found = _simca_steps(estimator)
+    if not found:
         raise AttributeError("Pipeline without a SIMCA step: cannot locate n_components.")
-    return "n_components"
+    return found[0][0] + "n_components"
 
 
 def _percent_metrics(TP, TN, FP, FN):
