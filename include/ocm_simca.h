@@ -189,10 +189,29 @@ int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
                         const float* mu, const float* P, const float* Sinv,
                         const ocm_score_params* h_params,
                         float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
+/* fp64 rows (numpy's default dtype).  Bulk shapes (the fp32 gate below on n, p, n_components; 16-byte aligned rows
+ * and mean; scores == NULL) are centred -- and SNV-normalised when asked -- in fp64, rounded once to fp32 into a bounded
+ * stream-ordered scratch buffer (1 GB chunks by default, a memory pool of the library's own) and scored chunk by chunk on
+ * the tcgen05 kernels; anything
+ * else runs on the generic kernel, which rounds at the same point. */
 int ocm_simca_score_f64in(const double* X, int64_t n, int32_t p, int64_t ldx,
                           const double* mu, const float* P, const float* Sinv,
                           const ocm_score_params* h_params,
                           float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
+int ocm_simca_score_f64in_bulk_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, const void* X, const void* mu);
+/* fp32 rows with fused SNV at shapes whose plain form the tcgen05 kernels take but whose fused form they do not
+ * (1152 < p <= 2048): ocm_simca_score_f32 stages SNV + centring (ocm_preprocess_f32, OCM_PRE_SNV_CENTER) through the same
+ * scratch and scores the chunk on the cluster kernel.  The scratch pool is released by ocm_simca_host_release. */
+int ocm_simca_score_snv_staged_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, const void* X, const void* mu);
+int ocm_simca_score_snv_staged_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
+                                   const float* mu, const float* P, const float* Sinv,
+                                   const ocm_score_params* h_params,
+                                   float* T2, float* Q, uint8_t* accept, void* stream);
+/* the fp64 contract above, forced onto the generic kernel */
+int ocm_simca_score_simt_f64in(const double* X, int64_t n, int32_t p, int64_t ldx,
+                               const double* mu, const float* P, const float* Sinv,
+                               const ocm_score_params* h_params,
+                               float* T2, float* Q, uint8_t* accept, float* scores, void* stream);
 /* same contract, forced onto the FP32-pipe kernel (any shape; the dispatcher above picks the
  * tcgen05 kernel when the shape allows it) */
 int ocm_simca_score_simt_f32(const float* X, int64_t n, int32_t p, int64_t ldx,
@@ -209,7 +228,7 @@ int ocm_simca_score_rowteam_f32(const float* X, int64_t n, int32_t p, int64_t ld
                                 float* T2, float* Q, uint8_t* accept, void* stream);
 
 /* 1 when ocm_simca_score_f32 would take a tcgen05/TMA kernel for this shape (bulk path: fp32 rows, 64 <= p <= 2048, p a
- * multiple of 4, n_components <= 16, 16-byte aligned rows, no fused SNV, n >= 32768), else 0. */
+ * multiple of 4, n_components <= 16, 16-byte aligned rows, n >= 32768; fused SNV up to p = 1152), else 0. */
 int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
 /* the tcgen05 kernels themselves: p <= 1152 runs one CTA per 128-spectrum tile (score_tc.cu; fp16 operand mode when
  * h_params->x_rms > 0), wider spectra the cluster kernel below with four CTAs per tile */

@@ -12,6 +12,11 @@ extern "C" int ocm_simca_score_rowteam_supported(int64_t n, int32_t p, int64_t l
 extern "C" int ocm_simca_score_rowteam_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
                                            const float*, const ocm_score_params*, float*, float*, uint8_t*, void*);
 
+extern "C" int ocm_simca_score_snv_staged_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, const void* X, const void* mu);
+extern "C" int ocm_simca_score_snv_staged_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*,
+                                              const float*, const ocm_score_params*, float*, float*, uint8_t*, void*);
+extern "C" int ocm_simca_staged_release(void);
+
 extern "C" int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t ldx, const float* mu,
                                    const float* P, const float* Sinv, const ocm_score_params* hp,
                                    float* T2, float* Q, uint8_t* accept, float* scores, void* stream) {
@@ -19,6 +24,9 @@ extern "C" int ocm_simca_score_f32(const float* X, int64_t n, int32_t p, int64_t
     OCM_REQUIRE(hp, OCM_EINVAL, "NULL params");
     if (!scores && ocm_simca_score_tc_supported(n, p, ldx, hp->A, hp->snv, X))
         return ocm_simca_score_tc_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, stream);
+    // fused SNV wider than the tcgen05 kernel fuses it: SNV + centring staged through a scratch chunk, then the bulk kernel
+    if (!scores && hp->snv && ocm_simca_score_snv_staged_supported(n, p, ldx, hp->A, X, mu))
+        return ocm_simca_score_snv_staged_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, stream);
     if (!scores && ocm_simca_score_rowteam_supported(n, p, ldx, hp->A, hp->snv, X) &&
         (reinterpret_cast<uintptr_t>(mu) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0)
         return ocm_simca_score_rowteam_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, stream);
@@ -67,6 +75,7 @@ extern "C" int ocm_simca_host_release(void) {
         g_ws[d].release();
     }
     cudaSetDevice(cur);
+    ocm_simca_staged_release();
     return 0;
 }
 

@@ -303,9 +303,9 @@ extern "C" int ocm_simca_score_simt_f32(const float* X, int64_t n, int32_t p, in
                                         float* T2, float* Q, uint8_t* accept, float* scores, void* stream) {
     return ocm::score_single<float>(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
 }
-extern "C" int ocm_simca_score_f64in(const double* X, int64_t n, int32_t p, int64_t ldx, const double* mu,
-                                     const float* P, const float* Sinv, const ocm_score_params* hp,
-                                     float* T2, float* Q, uint8_t* accept, float* scores, void* stream) {
+extern "C" int ocm_simca_score_simt_f64in(const double* X, int64_t n, int32_t p, int64_t ldx, const double* mu,
+                                          const float* P, const float* Sinv, const ocm_score_params* hp,
+                                          float* T2, float* Q, uint8_t* accept, float* scores, void* stream) {
     return ocm::score_single<double>(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
 }
 extern "C" int ocm_simca_score_multiA_f32(const float* X, int64_t n, int32_t p, int64_t ldx, const float* mu,

@@ -547,6 +547,90 @@ def test_fused_snv_on_the_tensor_core_kernel(torch):
             assert_decisions(acc.cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
 
 
+def test_fused_snv_wide_spectra_are_staged(torch):
+    """Fused SNV wider than the tcgen05 kernel fuses it (p > 1152): SNV + centring staged through the scratch chunk, then
+    the cluster kernel -- against SNV + scoring in fp64 on the same fp32 inputs and against the generic kernel."""
+    dev = torch.device("cuda"); lib = native.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr()); st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, A, p in ((40_000, 10, 2048), (70_003, 6, 1600)):
+        Xraw = synth.make_spectra_device(n, p, dev, seed=p % 53 + A)
+        g = torch.Generator(device=dev); g.manual_seed(1000 + p)
+        Xraw = Xraw * (1.0 + 0.3 * torch.rand(n, 1, device=dev, generator=g)) + 0.5 * torch.rand(n, 1, device=dev, generator=g)
+        X64 = Xraw.double()
+        Xs = (X64 - X64.mean(1, keepdim=True)) / (X64.std(1, unbiased=False, keepdim=True) + 1e-8)
+        pca = engine.fit_pca(Xs[:3000].contiguous(), None, A)
+        Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+        mu32, P32 = pca.arrays32(); S32 = Sinv.float().contiguous()
+        assert lib.ocm_simca_score_tc_supported(n, p, p, A, 1, vp(Xraw)) == 0
+        assert lib.ocm_simca_score_snv_staged_supported(n, p, p, A, vp(Xraw), vp(mu32)) == 1
+        sub = slice(None, None, 5)
+        model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+        T2r, Qr = so.score(model, Xs[sub].cpu().numpy())
+        prm = native.ScoreParams(A=A, rule=1, snv=1, snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)), x_rms=pca.x_rms)
+        outs = []
+        for fn in (lib.ocm_simca_score_f32, lib.ocm_simca_score_simt_f32):
+            T2 = torch.full((n,), -1.0, device=dev); Q = torch.full((n,), -1.0, device=dev); acc = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+            native.check(fn(vp(Xraw), n, p, p, vp(mu32), vp(P32), vp(S32), C.byref(prm), vp(T2), vp(Q), vp(acc), None, st))
+            assert lib.ocm_simca_score_tc_status() == 0
+            outs.append((T2, Q, acc))
+        msg = f"n={n} A={A} p={p}"
+        T2, Q, acc = outs[0]
+        np.testing.assert_allclose(T2[sub].cpu().numpy(), T2r, rtol=2e-4, atol=4e-7 * A, err_msg=msg)      # fp32 row statistics
+        np.testing.assert_allclose(Q[sub].cpu().numpy(), Qr, rtol=2e-4, err_msg=msg)
+        d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
+        assert_decisions(acc[sub].cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2), tol=5e-4)
+        assert float(((T2 - outs[1][0]).abs() / (outs[1][0] + 4e-7 * A)).max()) < 5e-4, msg
+        assert float(((Q - outs[1][1]).abs() / outs[1][1]).max()) < 5e-4, msg
+
+
+def test_fp64_rows_take_the_bulk_path(torch):
+    """fp64 spectra (numpy's default, what utils/SIMCA.py:127 receives) at bulk shapes: centred / SNV-normalised in fp64,
+    rounded once, scored on the tcgen05 kernels chunk by chunk -- against the fp64 arithmetic and the generic kernel;
+    one shape spans several scratch chunks with a ragged tail."""
+    dev = torch.device("cuda"); lib = native.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr()); st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, A, p, snv in ((40_000, 10, 1024, False), (140_003, 6, 1024, False), (33_000, 12, 2048, False),
+                         (36_000, 5, 512, True), (70_001, 9, 700, True)):
+        g = torch.Generator(device=dev); g.manual_seed(n + p)
+        X = synth.make_spectra_device(n, p, dev, seed=n % 89 + A).double()
+        X += 1e-9 * torch.randn(n, p, device=dev, dtype=torch.float64, generator=g)        # bits below fp32 resolution
+        if snv:
+            X = X * (1.0 + 0.3 * torch.rand(n, 1, device=dev, dtype=torch.float64, generator=g)) + 0.5
+            Xs = (X - X.mean(1, keepdim=True)) / (X.std(1, unbiased=False, keepdim=True) + 1e-8)
+        else:
+            Xs = X
+        pca = engine.fit_pca(Xs[:3000].contiguous(), None, A)
+        Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+        assert lib.ocm_simca_score_f64in_bulk_supported(n, p, p, A, vp(X), vp(pca.mean)) == 1
+        sub = slice(None, None, 7)
+        model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+        T2r, Qr = so.score(model, Xs[sub].cpu().numpy())
+        l0 = native.launch_count()
+        os.environ["OCM_STAGED_SCRATCH_MB"] = "256"          # 65 536 rows of 1024 wavelengths per chunk (default: 1 GB)
+        try:
+            T2, Q, acc = engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=50.0, dlim=np.sqrt(2), snv=snv,
+                                      x_rms=pca.x_rms)
+        finally:
+            del os.environ["OCM_STAGED_SCRATCH_MB"]
+        assert lib.ocm_simca_score_tc_status() == 0
+        chunks = 2 if n == 140_003 else 1                    # 65 536 + a tail of 74 467 (no tail below the bulk gate)
+        assert 2 * chunks <= native.launch_count() - l0 <= 3 * chunks      # conversion + bulk kernel (+ fp16-mode fix-up) per chunk
+        msg = f"n={n} A={A} p={p} snv={snv}"
+        np.testing.assert_allclose(T2[sub].cpu().numpy(), T2r, rtol=RTOL, atol=2e-7 * A, err_msg=msg)
+        np.testing.assert_allclose(Q[sub].cpu().numpy(), Qr, rtol=RTOL, err_msg=msg)
+        d = np.sqrt((T2r * 0.05) ** 2 + (Qr * 50.0) ** 2)
+        assert_decisions(acc[sub].cpu().numpy().astype(float), (d < np.sqrt(2)).astype(float), d, np.sqrt(2))
+        # every row against the generic kernel's fp64 path (same rounding point without SNV)
+        prm = native.ScoreParams(A=A, rule=1, snv=int(snv), snv_eps=1e-8, ct=0.05, cq=50.0, dlim=float(np.sqrt(2)))
+        T2g = torch.empty(n, device=dev); Qg = torch.empty(n, device=dev); accg = torch.empty(n, dtype=torch.uint8, device=dev)
+        mu64, (_, P32) = pca.mean.contiguous(), pca.arrays32(); S32 = Sinv.float().contiguous()
+        native.check(lib.ocm_simca_score_simt_f64in(vp(X), n, p, p, vp(mu64), vp(P32), vp(S32), C.byref(prm),
+                                                    vp(T2g), vp(Qg), vp(accg), None, st))
+        tol = 3e-4 if snv else 3e-5          # the generic kernel's SNV statistics are fp32
+        assert float(((T2 - T2g).abs() / (T2g + 2e-7 * A)).max()) < tol, msg
+        assert float(((Q - Qg).abs() / Qg).max()) < tol, msg
+
+
 def test_scoring_properties_at_bulk_shape(torch):
     """Size-independent properties at p=1024, A=10 on 300k device-generated rows."""
     dev = torch.device("cuda")
