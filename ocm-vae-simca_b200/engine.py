@@ -526,6 +526,9 @@ def fit_pca_folds(X, row_sets, k) -> list:
     w, V, tails, conv = eig_topk_subspace(Cs, k)
     w_h, tails_h, conv_h = w[:, :k].cpu().numpy(), tails.cpu().numpy(), conv.cpu().numpy()
     P_all = sign_normalise_(V[:, :, :k].transpose(1, 2).contiguous())      # [F(+1), k, p], one batched pass
+    P32_all = P_all.to(torch.float32)                                      # what the scoring launches read: converted once, not per fold
+    inv_all = 1.0 / w[:, :k].clamp_min(0.0)
+    inv32_all = inv_all.to(torch.float32)
     models = []
     for f in range(len(row_sets)):
         if not conv_h[f]:
@@ -534,7 +537,8 @@ def fit_pca_folds(X, row_sets, k) -> list:
         P = P_all[f]
         lam = np.maximum(w_h[f], 0.0)
         models.append(PCAModel(mean=means[f], P=P, eigs_all=Spectrum(lam, np.maximum(tails_h[f], 0.0)), n_samples=ns[f]))
-        models[-1].inv_eig_device = 1.0 / w[f, :k].clamp_min(0.0)      # stays on the device for the multi-A scoring launch
+        models[-1].inv_eig_device = inv_all[f]      # stays on the device for the multi-A scoring launch
+        models[-1].P32, models[-1].inv_eig32 = P32_all[f], inv32_all[f]
     fit_pca_folds.last_pool = None
     if pool is not None and conv_h[-1]:
         from .limits import LazySpectrum

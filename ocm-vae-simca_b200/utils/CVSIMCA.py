@@ -210,7 +210,8 @@ def _run_batched(estimator, X, y, splits, combos, lv_of_combo, ncomp_in_grid, st
                 lim_h[k_f, 2, A - 1] = lim.D_limit
         lim_d = torch.as_tensor(lim_h, device=Xd.device)
         for k_f, (fi, f) in enumerate(zip(mine, fm.folds)):
-            _, _, acc = engine.score_multiA(f["Xte"], f["pca"].mean, f["pca"].P, f["inv_eig"], rule=prm["type"],
+            _, _, acc = engine.score_multiA(f["Xte"], f["pca"].mean, getattr(f["pca"], "P32", f["pca"].P),
+                                            getattr(f["pca"], "inv_eig32", f["inv_eig"]), rule=prm["type"],
                                             ct=lim_d[k_f, 0], cq=lim_d[k_f, 1], dlim=lim_d[k_f, 2])
             acc = acc.index_select(1, cols).contiguous()
             pooled[f["te_idx"]] = acc
