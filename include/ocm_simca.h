@@ -292,12 +292,22 @@ int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_t ldz,
 /* ---- host-buffer convenience (the end-to-end call bench.py times as `e2e`) -------------
  * Scores h_X (HOST, pageable or pinned) in row chunks (chunk_rows <= 0: 65536), overlapping H2D copies with the
  * kernel on two internal streams, and writes h_T2 / h_Q / h_accept (HOST).  Synchronises before returning.  Its
- * device staging buffers and streams are a per-process workspace kept between calls (calls are serialised);
- * ocm_simca_host_release() frees it. */
+ * device staging buffers and streams are a per-device workspace kept between calls (calls on one device are serialised);
+ * ocm_simca_host_release() frees it.
+ * Pinned fp32 rows are copied straight from the caller's buffer.  Pageable rows (a numpy array) and fp64 rows go through
+ * two pinned bounce buffers that host threads fill in parallel (OCM_HOST_THREADS, default min(cores, 16)) while the
+ * previous chunk is on the link; fp64 rows are centred in fp64 and rounded once during that fill -- (float)(x - mu), the
+ * rounding point of ocm_simca_score_f64in -- so 4 bytes per element cross the link (with fused SNV: rounded, then
+ * normalised and centred by the kernel).  This is what utils/SIMCA.py:120-154 (predict) and :101-117 (transform) amount to
+ * for a numpy matrix that does not fit, or is not worth holding, in device memory. */
 int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, int64_t ldx,
                              const float* h_mu, const float* h_P, const float* h_Sinv,
                              const ocm_score_params* h_params, int64_t chunk_rows,
                              float* h_T2, float* h_Q, uint8_t* h_accept);
+int ocm_simca_score_host_f64in(const double* h_X, int64_t n, int32_t p, int64_t ldx,
+                               const double* h_mu, const float* h_P, const float* h_Sinv,
+                               const ocm_score_params* h_params, int64_t chunk_rows,
+                               float* h_T2, float* h_Q, uint8_t* h_accept);
 int ocm_simca_host_release(void);
 
 #ifdef __cplusplus

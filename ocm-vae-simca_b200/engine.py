@@ -646,6 +646,42 @@ def score(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=Fal
     return (T2, Q, acc, sc) if want_scores else (T2, Q, acc)
 
 
+HOST_STREAM_BYTES = 256 << 20      # host matrices above this are streamed through the host-buffer call, not uploaded whole
+
+
+def host_streamable(X):
+    """True for a host matrix that `score_host` takes as it is: 2-D numpy fp32 / fp64, unit column stride, above
+    HOST_STREAM_BYTES (smaller inputs are uploaded whole: one copy, one launch)."""
+    return (isinstance(X, np.ndarray) and X.ndim == 2 and X.dtype in (np.float32, np.float64) and X.shape[0] > 0
+            and X.strides[1] == X.itemsize and X.strides[0] >= X.shape[1] * X.itemsize and X.strides[0] % X.itemsize == 0
+            and X.nbytes > HOST_STREAM_BYTES)
+
+
+def score_host(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=False, snv_eps=1e-8, x_rms=0.0,
+               chunk_rows=0):
+    """Fused T2 / Q / accept for the rows of a HOST matrix (numpy fp32 or fp64, pageable or pinned) against one model,
+    streamed chunk by chunk over the link with the copies overlapping the kernel (ocm_simca_score_host_f32 / _f64in): the
+    matrix never has to fit in device memory.  Returns numpy (T2 fp32, Q fp32, accept uint8)."""
+    torch = native.require_cuda()
+    lib = native.lib()
+    n, p = X.shape
+    A = P.shape[0]
+    f64 = X.dtype == np.float64
+    mu_h = np.ascontiguousarray(mean.detach().cpu().numpy() if isinstance(mean, torch.Tensor) else mean,
+                                dtype=np.float64 if f64 else np.float32)
+    P_h = np.ascontiguousarray(P.detach().cpu().numpy() if isinstance(P, torch.Tensor) else P, dtype=np.float32)
+    S_h = np.ascontiguousarray(Sinv.detach().cpu().numpy() if isinstance(Sinv, torch.Tensor) else Sinv, dtype=np.float32)
+    T2 = np.empty(n, np.float32); Q = np.empty(n, np.float32); acc = np.empty(n, np.uint8)
+    prm = native.ScoreParams(A=A, rule=RULES[rule] if isinstance(rule, str) else int(rule), snv=int(bool(snv)),
+                             snv_eps=float(snv_eps), ct=float(ct), cq=float(cq), dlim=float(dlim), x_rms=float(x_rms or 0.0))
+    hp = lambda a: C.c_void_p(a.ctypes.data)
+    fn = lib.ocm_simca_score_host_f64in if f64 else lib.ocm_simca_score_host_f32
+    rc = fn(hp(X), n, p, X.strides[0] // X.itemsize, hp(mu_h), hp(P_h), hp(S_h), C.byref(prm), int(chunk_rows),
+            hp(T2), hp(Q), hp(acc))
+    native.check(rc, "ocm_simca_score_host")
+    return T2, Q, acc
+
+
 def score_multiA(X, mean, P, inv_eig, rule="alt", ct=None, cq=None, dlim=None, snv=False, snv_eps=1e-8):
     """All nested models A = 1..Amax at once.  Returns T2, Q [n,Amax] fp32 and accept [n,Amax] uint8
     (accept is None when no limits are given)."""

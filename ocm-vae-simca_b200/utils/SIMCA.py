@@ -270,8 +270,23 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         return engine.score(Xd, info["_pca"].mean, info["_pca"].P, info["_Sinv"], rule=self.type,
                             ct=ct, cq=cq, dlim=lim.D_limit, snv=snv, x_rms=getattr(info["_pca"], "x_rms", 0.0))
 
+    def _score_class_host(self, X, cls, snv=False):
+        """Same as _score_class for a large host matrix: streamed over the link chunk by chunk (engine.score_host),
+        results as numpy arrays."""
+        info = self._model[cls]
+        lim = info["_limits"]
+        ct, cq = lim.reduced_scales(self.type)
+        return engine.score_host(X, info["_pca"].mean, info["_pca"].P, info["_Sinv"], rule=self.type,
+                                 ct=ct, cq=cq, dlim=lim.D_limit, snv=snv, x_rms=getattr(info["_pca"], "x_rms", 0.0))
+
     def transform(self, X):
         """(T2, T2red, Q, Qred) of the LAST model class, as the reference returns (SIMCA.py:101-117)."""
+        if engine.host_streamable(X):
+            for cls in self.model_class:
+                T2, Q, _ = self._score_class_host(X, cls)
+                ct, cq = self._model[cls]["_limits"].reduced_scales(self.type)
+            T2h, Qh = T2.astype(np.float64), Q.astype(np.float64)
+            return T2h, T2h * ct, Qh, Qh * cq
         on_device = _is_cuda_tensor(X)
         Xd = engine.to_device(X)
         for cls in self.model_class:
@@ -288,13 +303,19 @@ class SIMCA(BaseEstimator, ClassifierMixin):
     def predict(self, X, y_true=None):
         """0./1. acceptance per model class, shape [N, n_classes] (SIMCA.py:120-154)."""
         on_device = _is_cuda_tensor(X)
-        Xd = engine.to_device(X)
-        torch = engine._torch()
-        out = torch.empty((Xd.shape[0], len(self.model_class)), dtype=torch.float64, device=Xd.device)
-        for i, cls in enumerate(self.model_class):
-            _, _, acc = self._score_class(Xd, cls)
-            out[:, i] = acc
-        predictions = out if on_device else out.cpu().numpy()
+        if engine.host_streamable(X):
+            # a large numpy matrix is streamed over the link (never resident as a whole); decisions come back per class
+            predictions = out = np.empty((X.shape[0], len(self.model_class)), dtype=np.float64)
+            for i, cls in enumerate(self.model_class):
+                out[:, i] = self._score_class_host(X, cls)[2]
+        else:
+            Xd = engine.to_device(X)
+            torch = engine._torch()
+            out = torch.empty((Xd.shape[0], len(self.model_class)), dtype=torch.float64, device=Xd.device)
+            for i, cls in enumerate(self.model_class):
+                _, _, acc = self._score_class(Xd, cls)
+                out[:, i] = acc
+            predictions = out if on_device else out.cpu().numpy()
         if y_true is not None:
             yt = y_true.detach().cpu().numpy() if hasattr(y_true, "detach") else np.asarray(y_true)
             pr = out.cpu().numpy() if on_device else predictions

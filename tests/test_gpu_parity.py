@@ -939,6 +939,48 @@ def test_host_buffer_api_bulk_chunks_take_the_tensor_core_kernel(torch):
     assert_decisions(acc.astype(float), so.predict(ref, X.astype(np.float64)), so.reduced_distance(ref, T2r, Qr), ref["D_limit"])
 
 
+def test_large_numpy_matrices_are_streamed(torch):
+    """SIMCA.predict / transform on a numpy matrix above engine.HOST_STREAM_BYTES (utils/SIMCA.py:101-154 on host arrays):
+    streamed through the pinned bounce buffers of the host-buffer call, pageable fp32 and fp64 rows, and bit-identical to
+    the same rows scored from device memory (same kernels, same rounding point for fp64)."""
+    n, p, A = 80_000, 1024, 8
+    dev = torch.device("cuda")
+    X32 = synth.make_spectra(n, p, seed=33).astype(np.float32)
+    y = np.zeros(n, int); y[n // 2:] = 1
+    X32[n // 2:] += 0.02 * np.linspace(0, 1, p, dtype=np.float32)
+    for X in (X32, X32.astype(np.float64) + 1e-9):
+        model = SIMCA(n_components=A, model_class=0, verbose=False).fit(X[:4000], y[:4000])
+        assert engine.host_streamable(X) and not engine.host_streamable(X[:1000])
+        l0 = native.launch_count()
+        pred_h = model.predict(X)
+        T2h, T2rh, Qh, Qrh = model.transform(X)
+        assert native.launch_count() - l0 >= 4                      # two chunks per call, at least one kernel each
+        assert isinstance(pred_h, np.ndarray) and pred_h.shape == (n, 1) and pred_h.dtype == np.float64
+        Xd = torch.as_tensor(X, device=dev)
+        pred_d = model.predict(Xd).cpu().numpy()
+        T2d, T2rd, Qd, Qrd = [t.double().cpu().numpy() for t in model.transform(Xd)]
+        assert np.array_equal(pred_h, pred_d), str(X.dtype)
+        assert np.array_equal(T2h, T2d) and np.array_equal(Qh, Qd), str(X.dtype)
+        np.testing.assert_allclose(T2rh, T2rd, rtol=1e-6); np.testing.assert_allclose(Qrh, Qrd, rtol=1e-6)
+        sub = slice(None, None, 9)
+        info = model._model[0]
+        ref = dict(pred_mean=info["xmean"], pred_P=info["P"], Sinv=info["invcovT"])
+        T2r, Qr = so.score(ref, X[sub].astype(np.float64))
+        np.testing.assert_allclose(T2h[sub], T2r, rtol=RTOL, atol=2e-7 * A)
+        np.testing.assert_allclose(Qh[sub], Qr, rtol=RTOL)
+        del Xd
+    # fp64 rows with fused SNV: rounded to fp32 on the host threads, normalised and centred by the kernel
+    X64 = X32[:70_000].astype(np.float64) * (1.0 + 0.3 * np.random.default_rng(1).random((70_000, 1))) + 0.25
+    Xs = so.snv(X64)
+    ref = so.fit_one_class(Xs[:3000], 5)
+    T2r, Qr = so.score(ref, Xs[::11])
+    T2, Q, acc = engine.score_host(X64, ref["pred_mean"], ref["pred_P"], ref["Sinv"], rule="alt", ct=1.0 / ref["T2_limit"],
+                                   cq=1.0 / ref["Q_limit"], dlim=ref["D_limit"], snv=True)
+    np.testing.assert_allclose(T2[::11], T2r, rtol=3e-5, atol=4e-7 * 5)
+    np.testing.assert_allclose(Q[::11], Qr, rtol=3e-5)
+    assert native.lib().ocm_simca_host_release() == 0
+
+
 def test_cv_grid_folds_over_ranks(torch):
     """§8(e): folds dealt over two ranks (gloo, both on this GPU) give the single-process CV table on every rank."""
     import subprocess, sys, json
