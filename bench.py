@@ -686,6 +686,25 @@ def main():
                          "host_binding": numa},
                "api": "ocm_simca_score_host_f32 (pinned host X -> T2,Q,accept on host; chunked double-buffered H2D)",
                "check": {"accepted_first_chunk": int(hA[: 1 << 10].sum().item())}}
+        if world == 1:
+            # the same call on a plain numpy matrix (pageable memory: what SIMCA.predict receives from a reference user);
+            # reported next to the pinned figure, not instead of it
+            try:
+                Xnp = hX.numpy().copy()
+                hstep = lambda: engine.score_host(Xnp, pca.mean, pca.P, Sinv, rule="alt", ct=float(ct), cq=float(cq),
+                                                  dlim=float(lim.D_limit), x_rms=float(pca.x_rms))
+                hstep()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    acc_np = hstep()[2]
+                ndt = time.perf_counter() - t0
+                e2e["numpy_pageable"] = {"value": 2 * er / ndt, "unit": "spectra/s", "link_gbs": 2 * er * p * 4 / ndt / 1e9,
+                                         "api": "engine.score_host (SIMCA.predict on a large numpy matrix) -> ocm_simca_score_host_f32: "
+                                                "pageable rows through pinned bounce buffers filled by host threads",
+                                         "check": {"accepted_first_chunk": int(acc_np[: 1 << 10].sum())}}
+                del Xnp
+            except Exception as e:
+                e2e["numpy_pageable"] = {"error": repr(e)}
         del hX
 
     del X

@@ -308,6 +308,12 @@ int ocm_simca_score_host_f64in(const double* h_X, int64_t n, int32_t p, int64_t 
                                const double* h_mu, const float* h_P, const float* h_Sinv,
                                const ocm_score_params* h_params, int64_t chunk_rows,
                                float* h_T2, float* h_Q, uint8_t* h_accept);
+/* Pageable (or pinned) host rows -> device rows through the same workspace: n rows of row_bytes bytes, strides in bytes.
+ * Pageable sources are copied into the pinned bounce buffers by the host threads while the previous chunk is on the link
+ * (a plain cudaMemcpy of pageable memory is staged by the driver on one thread: ~11 GB/s on the B200 box against ~37).
+ * Blocking: the data is complete on return. */
+int ocm_upload_rows(const void* h_src, int64_t n, int64_t row_bytes, int64_t src_stride_bytes,
+                    void* d_dst, int64_t dst_stride_bytes);
 int ocm_simca_host_release(void);
 
 #ifdef __cplusplus

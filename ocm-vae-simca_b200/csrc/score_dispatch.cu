@@ -272,6 +272,74 @@ extern "C" int ocm_simca_host_release(void) {
     return 0;
 }
 
+// Pageable host rows -> device rows at the rate of the parallel bounce fill (the same workspace): what engine.to_device
+// uses for a large numpy matrix in front of fit / CV / preprocessing.  Blocking; the data is complete on return.
+extern "C" int ocm_upload_rows(const void* h_src, int64_t n, int64_t row_bytes, int64_t src_stride,
+                               void* d_dst, int64_t dst_stride) {
+    using namespace ocm;
+    if (n == 0) return 0;
+    OCM_REQUIRE(h_src && d_dst && n > 0 && row_bytes > 0 && src_stride >= row_bytes && dst_stride >= row_bytes, OCM_EINVAL,
+                "bad shape or NULL buffer");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        set_error("ocm_upload_rows: no usable current device");
+        return (int)cudaErrorInvalidDevice;
+    }
+    std::lock_guard<std::mutex> lock(g_ws_mutex[dev]);
+    HostWorkspace& w = g_ws[dev];
+#define OCM_TRY(call)                                                                        \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                   \
+        set_error("%s: %s", #call, cudaGetErrorString(e_)); w.release(); return (int)e_; } } while (0)
+    w.device = dev;
+    const char* src = static_cast<const char*>(h_src);
+    char* dst = static_cast<char*>(d_dst);
+    for (int b = 0; b < 2; ++b) {
+        if (!w.st[b]) OCM_TRY(cudaStreamCreateWithFlags(&w.st[b], cudaStreamNonBlocking));
+        if (!w.ev_h2d[b]) OCM_TRY(cudaEventCreateWithFlags(&w.ev_h2d[b], cudaEventDisableTiming));
+    }
+    if (is_pinned(h_src)) {
+        OCM_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_stride, src, (size_t)src_stride, (size_t)row_bytes, (size_t)n,
+                                  cudaMemcpyHostToDevice, w.st[0]));
+        OCM_TRY(cudaStreamSynchronize(w.st[0]));
+        return 0;
+    }
+    int64_t rows = (64ll << 20) / row_bytes;
+    if (rows < 1) rows = 1;
+    if (rows > n) rows = n;
+    const size_t need = (size_t)rows * (size_t)row_bytes;
+    if (w.bounce_bytes < need) {
+        for (int b = 0; b < 2; ++b) { OCM_TRY(cudaFreeHost(w.h_X[b])); w.h_X[b] = nullptr; OCM_TRY(cudaMallocHost(&w.h_X[b], need)); }
+        w.bounce_bytes = need;
+    }
+    const int nt = fill_threads();
+    int b = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, b ^= 1) {
+        const int64_t m = (n - r0 < rows) ? n - r0 : rows;
+        OCM_TRY(cudaEventSynchronize(w.ev_h2d[b]));
+        char* bounce = reinterpret_cast<char*>(w.h_X[b]);
+        auto work = [=](int64_t a0, int64_t a1) {
+            if (src_stride == row_bytes) { memcpy(bounce + a0 * row_bytes, src + (r0 + a0) * src_stride, (size_t)(a1 - a0) * row_bytes); return; }
+            for (int64_t r = a0; r < a1; ++r) memcpy(bounce + r * row_bytes, src + (r0 + r) * src_stride, (size_t)row_bytes);
+        };
+        int t_use = nt > m ? (int)m : nt;
+        if ((int64_t)m * row_bytes < (4 << 20)) t_use = 1;
+        const int64_t per = (m + t_use - 1) / t_use;
+        std::vector<std::thread> th;
+        for (int t = 1; t < t_use; ++t) {
+            const int64_t a0 = t * per, a1 = (a0 + per < m) ? a0 + per : m;
+            if (a0 < a1) th.emplace_back(work, a0, a1);
+        }
+        work(0, per < m ? per : m);
+        for (auto& t : th) t.join();
+        OCM_TRY(cudaMemcpy2DAsync(dst + r0 * dst_stride, (size_t)dst_stride, bounce, (size_t)row_bytes, (size_t)row_bytes, (size_t)m,
+                                  cudaMemcpyHostToDevice, w.st[b]));
+        OCM_TRY(cudaEventRecord(w.ev_h2d[b], w.st[b]));
+    }
+    for (int k = 0; k < 2; ++k) OCM_TRY(cudaStreamSynchronize(w.st[k]));
+#undef OCM_TRY
+    return 0;
+}
+
 extern "C" int ocm_simca_score_host_f32(const float* h_X, int64_t n, int32_t p, int64_t ldx,
                                         const float* h_mu, const float* h_P, const float* h_Sinv,
                                         const ocm_score_params* hp, int64_t chunk_rows,

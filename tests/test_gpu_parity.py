@@ -969,6 +969,12 @@ def test_large_numpy_matrices_are_streamed(torch):
         np.testing.assert_allclose(T2h[sub], T2r, rtol=RTOL, atol=2e-7 * A)
         np.testing.assert_allclose(Qh[sub], Qr, rtol=RTOL)
         del Xd
+    # engine.to_device of a large numpy matrix goes through the same bounce buffers (ocm_upload_rows): exact copies
+    Xpad = np.zeros((30_000, 1100), np.float32); Xpad[:, :1024] = X32[:30_000]
+    for a in (X32, X32[:20_000].astype(np.float64), Xpad[:, :1024], X32[:17_000, :700]):
+        t = engine.to_device(a)
+        assert t.is_cuda and tuple(t.shape) == a.shape and t.stride(1) == 1
+        assert torch.equal(t.cpu(), torch.from_numpy(np.ascontiguousarray(a)))
     # fp64 rows with fused SNV: rounded to fp32 on the host threads, normalised and centred by the kernel
     X64 = X32[:70_000].astype(np.float64) * (1.0 + 0.3 * np.random.default_rng(1).random((70_000, 1))) + 0.25
     Xs = so.snv(X64)

@@ -1,5 +1,5 @@
 """Launch every hot kernel of the library a few times on representative shapes (for ncu: `-k regex:...` picks one).
-usage: python tools/kernels_once.py [score|gram|small|all]"""
+usage: python tools/kernels_once.py [score|gram|f64|all]"""
 import sys
 import numpy as np
 import torch
@@ -55,5 +55,14 @@ if what in ("gram", "all"):
     for _ in range(2):
         engine.gram_tc(X, None, s / cnt, mn, mx, products=13)
     engine.gram(X[:50_000], None, s / cnt)
+    torch.cuda.synchronize()
+if what == "f64":
+    # fp64 rows on the staged bulk path: fp64 centring -> fp32 scratch -> tcgen05 kernel
+    n, p, A = 500_000, 1024, 10
+    X = synth.make_spectra_device(n, p, dev, seed=7).double()
+    pca = engine.fit_pca(X[:5000].contiguous(), None, A)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+    for snv in (False, False, True):
+        engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=100.0, x_rms=pca.x_rms, snv=snv)
     torch.cuda.synchronize()
 print("ok")
