@@ -155,7 +155,7 @@ int score_host_impl(const TIn* h_X, int64_t n, int32_t p, int64_t ldx, const TIn
     w.device = dev;
     const bool bounce = F64 || !is_pinned(h_X);             // through the pinned bounce buffers (parallel fill)
     const bool out_pinned = (!h_T2 || is_pinned(h_T2)) && (!h_Q || is_pinned(h_Q)) && (!h_accept || is_pinned(h_accept));
-    const bool bounce_out = bounce && !out_pinned;          // a D2H copy into pageable memory would block the host on the kernel
+    const bool bounce_out = !out_pinned;                    // a D2H copy into pageable memory would block the host on the kernel
     const size_t need_x = sizeof(float) * (size_t)chunk_rows * p, need_model = 2 * (size_t)p + (size_t)A * p + (size_t)A * A;
     for (int b = 0; b < 2; ++b) {
         if (!w.st[b]) OCM_TRY(cudaStreamCreateWithFlags(&w.st[b], cudaStreamNonBlocking));
@@ -223,9 +223,9 @@ int score_host_impl(const TIn* h_X, int64_t n, int32_t p, int64_t ldx, const TIn
     int b = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, b ^= 1) {
         const int64_t m = (n - r0 < chunk_rows) ? n - r0 : chunk_rows;
+        if (bounce_out) OCM_TRY(deliver(b));                // results of the chunk that used this slot two chunks ago
         if (bounce) {
             OCM_TRY(cudaEventSynchronize(w.ev_h2d[b]));     // the copy that last read this bounce buffer has finished
-            if (bounce_out) OCM_TRY(deliver(b));
             fill_rows<TIn>(w.h_X[b], h_X + r0 * ldx, m, p, ldx, centre_on_host ? mu64.data() : nullptr, nt);
             OCM_TRY(cudaMemcpyAsync(w.d_X[b], w.h_X[b], sizeof(float) * (size_t)m * p, cudaMemcpyHostToDevice, w.st[b]));
             OCM_TRY(cudaEventRecord(w.ev_h2d[b], w.st[b]));

@@ -21,6 +21,8 @@ extern "C" int ocm_simca_score_simt_f64in(const double*, int64_t, int32_t, int64
 extern "C" int ocm_simca_score_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*, const float*,
                                    const ocm_score_params*, float*, float*, uint8_t*, float*, void*);
 extern "C" int ocm_simca_score_tc_supported(int64_t n, int32_t p, int64_t ldx, int32_t A, int32_t snv, const void* X);
+extern "C" int ocm_simca_score_simt_f32(const float*, int64_t, int32_t, int64_t, const float*, const float*, const float*,
+                                        const ocm_score_params*, float*, float*, uint8_t*, float*, void*);
 
 namespace ocm {
 namespace staged {
@@ -71,6 +73,7 @@ centre_f64_kernel(const double* __restrict__ X, int64_t n, int p, int64_t ldx, c
 }
 
 constexpr int64_t kMinBulkRows = 32768;               // the tcgen05 gate (ocm_simca_score_tc_supported)
+constexpr int kNoScratch = -1000;                     // internal: no scratch chunk available, nothing has been launched
 constexpr int kMaxDevices = 64;
 
 int64_t scratch_bytes() {                             // fp32 scratch per chunk (+ up to 32 767 rows for the last one)
@@ -116,9 +119,12 @@ int score_chunks(int64_t n, int32_t p, const float* P, const float* Sinv, const 
     const size_t zero_bytes = ((size_t)p * sizeof(float) + 255) & ~(size_t)255;
     cudaMemPool_t pool = nullptr;
     int rc = scratch_pool(&pool);
-    if (rc) return rc;
+    if (rc) return kNoScratch;
     char* ws = nullptr;
-    OCM_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws), zero_bytes + (size_t)cap * p * sizeof(float), pool, st));
+    if (cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws), zero_bytes + (size_t)cap * p * sizeof(float), pool, st) != cudaSuccess) {
+        cudaGetLastError();                             // no scratch to be had (memory, or a driver without pools):
+        return kNoScratch;                              // the caller scores on the generic kernel instead
+    }
     float* zero_mu = reinterpret_cast<float*>(ws);
     float* xc = reinterpret_cast<float*>(ws + zero_bytes);
     rc = (int)cudaMemsetAsync(zero_mu, 0, zero_bytes, st);
@@ -169,13 +175,15 @@ extern "C" int ocm_simca_score_f64in(const double* X, int64_t n, int32_t p, int6
         return ocm_simca_score_simt_f64in(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
     const int snv = hp->snv;
     const double eps = (double)hp->snv_eps;
-    return score_chunks(n, p, P, Sinv, hp, T2, Q, accept, stream, [&](int64_t r0, int64_t m, float* xc) {
+    const int rc = score_chunks(n, p, P, Sinv, hp, T2, Q, accept, stream, [&](int64_t r0, int64_t m, float* xc) {
         const int64_t want = (m + 7) / 8, most = (int64_t)sm_count() * 8;
         const unsigned blocks = (unsigned)(want < most ? want : most);
         if (snv) centre_f64_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(X + r0 * ldx, m, p, ldx, mu, eps, xc, p);
         else     centre_f64_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(X + r0 * ldx, m, p, ldx, mu, 0.0, xc, p);
         return check_launch("centre_f64_kernel");
     });
+    if (rc == kNoScratch) return ocm_simca_score_simt_f64in(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, scores, stream);
+    return rc;
 }
 
 // fp32 rows with fused SNV at a shape whose plain (snv = 0) form the tcgen05 kernels take but whose fused form they do
@@ -196,7 +204,9 @@ extern "C" int ocm_simca_score_snv_staged_f32(const float* X, int64_t n, int32_t
     OCM_REQUIRE(X && mu && P && Sinv && hp && hp->snv, OCM_EINVAL, "NULL buffer or snv == 0");
     OCM_REQUIRE(ocm_simca_score_snv_staged_supported(n, p, ldx, hp->A, X, mu), OCM_ELIMIT, "shape not supported by the staged SNV path");
     const float eps = hp->snv_eps;
-    return score_chunks(n, p, P, Sinv, hp, T2, Q, accept, stream, [&](int64_t r0, int64_t m, float* xc) {
+    const int rc = score_chunks(n, p, P, Sinv, hp, T2, Q, accept, stream, [&](int64_t r0, int64_t m, float* xc) {
         return ocm_preprocess_f32(X + r0 * ldx, m, p, ldx, OCM_PRE_SNV_CENTER, mu, nullptr, eps, xc, p, stream);
     });
+    if (rc == kNoScratch) return ocm_simca_score_simt_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, nullptr, stream);
+    return rc;
 }
