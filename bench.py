@@ -444,6 +444,7 @@ def vae_leg(args, device, group, rank, world, local_rank):
         dist.all_reduce(std, group=group); std /= world
     torch.manual_seed(0)
     vae = ConvVAE1D(L, d, mean.cpu().numpy(), std.cpu().numpy()).to(device)
+    vae.channels_last = True          # same parameters and arithmetic, 2-D channels-last execution (convvae.py)
     model = vae
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(vae, device_ids=[local_rank], gradient_as_bucket_view=True)
@@ -492,11 +493,13 @@ def vae_leg(args, device, group, rank, world, local_rank):
 
     d2_all = torch.empty(n, device=device); q_all = torch.empty(n, device=device)
 
+    from ocm_vae_simca_b200.vae import FrozenScorer
+    scorer = FrozenScorer(vae)            # bf16 inference copy of the trained module: BatchNorm folded, channels-last convolutions
+
     def score_pass():
         for r in range(0, n, Bs):
             xb = X[r:r + Bs]
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                d2, q, _ = latent_recon_scores(vae, xb, sample=False, recon_dtype=torch.bfloat16)
+            d2, q, _ = scorer(xb)
             d2_all[r:r + xb.shape[0]] = d2; q_all[r:r + xb.shape[0]] = q
     score_pass()
     torch.cuda.synchronize()
@@ -531,11 +534,12 @@ def vae_leg(args, device, group, rank, world, local_rank):
     return {"metric": "VAE-SIMCA spectra/s (ConvVAE1D latent 16, bf16)", "n_gpus": world, "rows_total": rows_total, "rows_per_gpu": n,
             "scaling": "strong (1 M rows in total, sharded)",
             "scoring": {"value": rows_total / (score_ms * 1e-3), "unit": "spectra/s", "ms_per_pass": score_ms, "batch": Bs,
-                        "what": "bf16 encoder + decoder (PyTorch cuDNN/cuBLAS) + fused latent T2 / reconstruction Q kernel, whole shard",
+                        "what": "bf16 encoder + decoder (PyTorch cuDNN/cuBLAS; vae.FrozenScorer: BatchNorm folded, weights cast once, channels-last "
+                                "2-D convolutions) + fused latent T2 / reconstruction Q kernel, whole shard",
                         "gpu_launches": int(launches), "accepted_frac_p95_rule": acc_frac},
             "training": {"value": world * Bt / (train_ms * 1e-3), "unit": "spectra/s", "ms_per_step": train_ms, "batch_per_gpu": Bt,
-                         "what": "DistributedDataParallel bf16-autocast step (fwd + bwd + NCCL gradient all-reduce + fused Adam)" if world > 1
-                                 else "bf16-autocast step (fwd + bwd + fused Adam)",
+                         "what": "DistributedDataParallel bf16-autocast step (fwd + bwd + NCCL gradient all-reduce + fused Adam), channels-last execution" if world > 1
+                                 else "bf16-autocast step (fwd + bwd + fused Adam), channels-last execution",
                          "parameters": int(sum(p_.numel() for p_ in vae.parameters())), "loss_after": final_loss},
             "epilogue_roofline": {"kernel": "latent_score_kernel<bf16 xrec>", "bound": "hbm", "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
                                   "peak": hbm, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / hbm,

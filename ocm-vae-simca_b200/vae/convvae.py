@@ -97,9 +97,37 @@ class ConvVAE1D(nn.Module):
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
 
+    # -- channels-last execution (opt-in: `vae.channels_last = True`) --------------------
+    # Same parameters, same state dict, same arithmetic: every Conv1d / ConvTranspose1d runs as a 2-D convolution with
+    # H = 1 on channels-last activations (the weights are unsqueezed VIEWS, so autograd and the optimiser see the module's
+    # own parameters).  That is the layout cuDNN's tensor-core kernels take without transposes: the bf16-autocast
+    # training step of config 5 goes from 81.8 to 51.2 ms (batch 4096 x 1024, one B200, tools/vae_train_tune.py).
+    channels_last = False
+
+    @staticmethod
+    def _run_channels_last(seq, x4):
+        for m in seq:
+            if isinstance(m, nn.ConvTranspose1d):
+                x4 = F.conv_transpose2d(x4, m.weight.unsqueeze(2), m.bias, stride=(1, m.stride[0]), padding=(0, m.padding[0]),
+                                        output_padding=(0, m.output_padding[0]))
+            elif isinstance(m, nn.Conv1d):
+                x4 = F.conv2d(x4, m.weight.unsqueeze(2), m.bias, stride=(1, m.stride[0]), padding=(0, m.padding[0]))
+            elif isinstance(m, nn.BatchNorm1d):
+                if m.training and m.track_running_stats and m.num_batches_tracked is not None:
+                    m.num_batches_tracked.add_(1)
+                x4 = F.batch_norm(x4, m.running_mean, m.running_var, m.weight, m.bias, m.training or not m.track_running_stats,
+                                  m.momentum if m.momentum is not None else 0.0, m.eps)
+            else:
+                x4 = m(x4)
+        return x4
+
     # -- reference-visible API ---------------------------------------------------------
     def encode(self, x):
-        h = self.encoder_conv(x.unsqueeze(1)).flatten(1)
+        if self.channels_last:
+            x4 = x.reshape(x.shape[0], 1, 1, -1).contiguous(memory_format=torch.channels_last)
+            h = self._run_channels_last(self.encoder_conv, x4).squeeze(2).flatten(1)
+        else:
+            h = self.encoder_conv(x.unsqueeze(1)).flatten(1)
         h = self.fc(h)
         return self.fc_mu(h), self.fc_logvar(h)
 
@@ -107,8 +135,12 @@ class ConvVAE1D(nn.Module):
         return mu + torch.randn_like(mu) * torch.exp(0.5 * logvar)
 
     def decode(self, z):
-        h = self.fc_dec(z).view(z.size(0), self._enc_out_channels, self._enc_out_length)
-        out = self.decoder_conv(h).squeeze(1)
+        if self.channels_last:
+            h = self.fc_dec(z).view(z.size(0), self._enc_out_channels, 1, self._enc_out_length)
+            out = self._run_channels_last(self.decoder_conv, h.contiguous(memory_format=torch.channels_last)).reshape(z.size(0), -1)
+        else:
+            h = self.fc_dec(z).view(z.size(0), self._enc_out_channels, self._enc_out_length)
+            out = self.decoder_conv(h).squeeze(1)
         n = out.shape[-1]
         if n > self.input_length:
             out = out[..., : self.input_length]

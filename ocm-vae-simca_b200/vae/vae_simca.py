@@ -161,6 +161,81 @@ def latent_recon_scores(vae, x, sample=False, recon_dtype=None):
     return d2, q, mu
 
 
+class FrozenScorer:
+    """Inference copy of a trained ConvVAE1D for the bulk scoring pass of config 5 (final_vaesimca.py:471-533): the
+    network stays PyTorch (cuDNN / cuBLAS), but as the scoring loop wants it -- eval-mode BatchNorm folded into the
+    convolutions, weights cast ONCE to `dtype` (no autocast casts per call), the 1-D convolutions run as 2-D ones
+    (H = 1) in channels-last memory format, which is the layout cuDNN's tensor-core kernels take without transposes.
+    Measured on a B200, batch 8192 x 1024: 4.4e5 spectra/s (autocast on the module) -> 5.5e5 (folded, bf16) -> 6.9e5
+    (+ channels-last).  `scorer(x)` returns (d2, q, mu) like `latent_recon_scores(vae, x, sample=False)`: deterministic
+    reconstruction dec(mu), one fused epilogue kernel (ocm_latent_score_f32).  The copy does not follow later
+    training of `vae`; build a new one after updating the weights or the calibration buffers."""
+
+    def __init__(self, vae, dtype=None):
+        import copy
+        import torch
+        from torch import nn
+        from torch.nn.utils.fusion import fuse_conv_bn_eval
+        if dtype is None:
+            dtype = torch.bfloat16
+        src = copy.deepcopy(vae).eval()
+        dev = src.spec_mean.device
+
+        def rebuild(seq):
+            mods, out, i = list(seq), [], 0
+            while i < len(mods):
+                m = mods[i]
+                if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
+                    tr = isinstance(m, nn.ConvTranspose1d)
+                    if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                        m = fuse_conv_bn_eval(m, mods[i + 1], transpose=tr)
+                        i += 1
+                    kw = dict(stride=(1, m.stride[0]), padding=(0, m.padding[0]))
+                    if tr:
+                        c = nn.ConvTranspose2d(m.in_channels, m.out_channels, (1, m.kernel_size[0]),
+                                               output_padding=(0, m.output_padding[0]), **kw)
+                    else:
+                        c = nn.Conv2d(m.in_channels, m.out_channels, (1, m.kernel_size[0]), **kw)
+                    c.weight.data = m.weight.data.unsqueeze(2).clone()
+                    c.bias.data = m.bias.data.clone() if m.bias is not None else torch.zeros_like(c.bias.data)
+                    out.append(c)
+                elif isinstance(m, nn.Dropout):
+                    pass                                  # identity in eval mode
+                else:
+                    out.append(m)
+                i += 1
+            return nn.Sequential(*out).to(device=dev, dtype=dtype).to(memory_format=torch.channels_last).eval()
+
+        self.dtype = dtype
+        self.enc, self.dec = rebuild(src.encoder_conv), rebuild(src.decoder_conv)
+        self.fc, self.fc_mu, self.fc_dec = src.fc.to(dtype), src.fc_mu.to(dtype), src.fc_dec.to(dtype)
+        self.L, self.C, self.Lenc = src.input_length, src._enc_out_channels, src._enc_out_length
+        self.spec_mean, self.spec_std = src.spec_mean.float(), src.spec_std.float()
+        self.mean_d, self.std_d = self.spec_mean.to(dtype), self.spec_std.to(dtype)
+        self.latent_mean, self.latent_cov_inv = src.latent_mean.float(), src.latent_cov_inv.float()
+
+    def encode_decode(self, x):
+        """(mu [n, d], x_rec [n, L]) in the scorer's dtype for fp32 rows x."""
+        import torch
+        with torch.no_grad():
+            xs = ((x - self.spec_mean) / self.spec_std).to(self.dtype)
+            h = self.enc(xs.view(-1, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
+            mu = self.fc_mu(self.fc(h.squeeze(2).flatten(1)))         # logical [n, C, L'] order, as `fc` was trained on
+            g = self.fc_dec(mu).view(-1, self.C, 1, self.Lenc).contiguous(memory_format=torch.channels_last)
+            xr = self.dec(g).reshape(x.shape[0], -1)
+            n = xr.shape[1]
+            if n > self.L:
+                xr = xr[:, : self.L]
+            elif n < self.L:
+                xr = torch.nn.functional.pad(xr, (0, self.L - n))
+            return mu, (xr * self.std_d + self.mean_d).contiguous()
+
+    def __call__(self, x):
+        mu, xr = self.encode_decode(x)
+        d2, q = engine.latent_score(z=mu.float(), m=self.latent_mean, Sinv=self.latent_cov_inv, x=x.float(), xrec=xr)
+        return d2, q, mu
+
+
 def compute_q_h_f(x, x_rec, z):
     """vae_model.py:162-181 on the device: q = |x - x_rec|^2; h = leverage of the batch-standardised
     latent (|U_i|^2 of its thin SVD == z_i (Z^T Z)^-1 z_i^T, evaluated by the Mahalanobis kernel);

@@ -1057,6 +1057,41 @@ def test_latent_score_and_vae_simca(torch, golden_dir):
         assert np.mean(yp.astype(np.uint8) != gv[tag + "::pred"]) < 0.03
 
 
+def test_frozen_scorer_matches_the_module_path(torch):
+    """vae.FrozenScorer (the bulk scoring copy of config 5) against latent_recon_scores on the module: fp32 copy to fp32
+    rounding, bf16 copy to bf16 rounding of the autocast path."""
+    from ocm_vae_simca_b200.vae import ConvVAE1D, FrozenScorer, latent_recon_scores
+    dev = torch.device("cuda")
+    L, d, n = 1024, 16, 4096
+    X = synth.make_spectra_device(n, L, dev, seed=77)
+    torch.manual_seed(1)
+    vae = ConvVAE1D(L, d, X.mean(0).cpu().numpy(), (X.std(0) + 1e-8).cpu().numpy()).to(dev)
+    vae.train()
+    with torch.no_grad():
+        for i in range(3):
+            vae(X[i * 512:(i + 1) * 512])                  # BatchNorm statistics away from their initial values
+    vae.eval()
+    with torch.no_grad():
+        mu_cal = vae.encode((X - vae.spec_mean) / vae.spec_std)[0]
+    Cm = torch.cov(mu_cal.T.double()) + 1e-6 * torch.eye(d, dtype=torch.float64, device=dev)
+    vae.latent_mean.copy_(mu_cal.mean(0)); vae.latent_cov_inv.copy_(torch.linalg.pinv(Cm).float())
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # fp32 means fp32 for this comparison
+    try:
+        d2r, qr, mur = latent_recon_scores(vae, X, sample=False)
+        d2, q, mu = FrozenScorer(vae, dtype=torch.float32)(X)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    np.testing.assert_allclose(mu.cpu().numpy(), mur.cpu().numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(q.cpu().numpy(), qr.cpu().numpy(), rtol=2e-3)
+    np.testing.assert_allclose(d2.cpu().numpy(), d2r.cpu().numpy(), rtol=5e-3, atol=1e-3)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        d2a, qa, _ = latent_recon_scores(vae, X, sample=False, recon_dtype=torch.bfloat16)
+    d2b, qb, _ = FrozenScorer(vae)(X)
+    assert float(((qb - qa).abs() / qa).median()) < 2e-2 and float(((qb - qr).abs() / qr).median()) < 5e-2
+    assert float(((d2b - d2a).abs() / (d2a + 1e-3)).median()) < 5e-2
+
+
 def test_smoke_entry(torch):
     import __graft_entry__ as ge
     ge.smoke()

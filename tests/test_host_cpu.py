@@ -207,3 +207,55 @@ def test_convvae_loads_both_reference_checkpoint_families():
     for k in a.state_dict():
         if not k.startswith("threshold"):
             assert torch.equal(c.state_dict()[k], a.state_dict()[k])
+
+
+def test_frozen_scorer_network_equals_the_module():
+    """vae.FrozenScorer (BatchNorm folded, 2-D channels-last convolutions) computes the module's encoder / deterministic
+    decoder: fp32 on the CPU, trained-looking BatchNorm statistics, a length the strides do not divide."""
+    import torch
+    from ocm_vae_simca_b200.vae import ConvVAE1D, FrozenScorer
+    torch.manual_seed(0)
+    for L, blocks in ((200, 3), (131, 2)):
+        vae = ConvVAE1D(L, 8, np.linspace(0, 1, L).astype(np.float32), np.full(L, 0.5, np.float32), conv_blocks=blocks,
+                        n_filters=8, hidden_fc=32, dropout=0.1)
+        vae.train()
+        for _ in range(3):
+            vae(torch.randn(16, L))
+        vae.eval()
+        fs = FrozenScorer(vae, dtype=torch.float32)
+        x = torch.randn(7, L)
+        mu, xr = fs.encode_decode(x)
+        with torch.no_grad():
+            xr0, mu0, _ = vae(x, sample=False)
+        assert xr.shape == xr0.shape
+        np.testing.assert_allclose(mu.numpy(), mu0.numpy(), atol=5e-6)
+        np.testing.assert_allclose(xr.numpy(), xr0.numpy(), atol=5e-6)
+
+
+def test_convvae_channels_last_mode_is_the_same_network():
+    """ConvVAE1D.channels_last = True (2-D channels-last execution of the same parameters) against the module as the
+    reference defines it: forward in train mode (batch statistics, running-stat updates), backward, eval mode."""
+    import torch
+    from ocm_vae_simca_b200.vae import ConvVAE1D
+    L = 96
+    mk = lambda: ConvVAE1D(L, 4, np.zeros(L, np.float32), np.ones(L, np.float32), conv_blocks=3, n_filters=4, hidden_fc=16)
+    torch.manual_seed(3)
+    a = mk(); b = mk(); b.load_state_dict(a.state_dict()); b.channels_last = True
+    x = torch.randn(12, L)
+    outs = []
+    for m in (a, b):
+        m.train()
+        mu, lv = m.encode(x)
+        xr = m.decode(mu)
+        (xr.square().mean() + mu.square().mean() + lv.mean()).backward()
+        outs.append((mu.detach(), xr.detach(), m.encoder_conv[0].weight.grad.clone(), m.decoder_conv[0].weight.grad.clone(),
+                     m.encoder_conv[1].running_mean.clone(), int(m.encoder_conv[1].num_batches_tracked)))
+    for u, v in zip(outs[0][:5], outs[1][:5]):
+        np.testing.assert_allclose(v.numpy(), u.numpy(), rtol=1e-4, atol=1e-5)
+    assert outs[0][5] == outs[1][5] == 1
+    a.eval(); b.eval()
+    with torch.no_grad():
+        ra, rb = a(x, sample=False), b(x, sample=False)
+    np.testing.assert_allclose(rb[0].numpy(), ra[0].numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rb[1].numpy(), ra[1].numpy(), rtol=1e-4, atol=1e-5)
+    assert set(a.state_dict()) == set(b.state_dict())
