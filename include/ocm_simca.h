@@ -289,6 +289,17 @@ int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_t ldz,
                          int32_t p, int64_t ldx, int64_t ldxrec,
                          float* d2, float* q, void* stream);
 
+/* ---- a15 / config 5: the elementwise-bound pieces of the ConvVAE1D scoring pass (vae_model.py:6-129 driven by
+ * utils/final_vaesimca.py:471-533), for channels-last bf16 activations [n][L][C].  act: 0 none, 1 ELU, 2 GELU (erf).
+ * ocm_vae_conv_in_bf16: first encoder block in one pass -- (x - spec_mean) / spec_std, Conv1d(1 -> C, K taps, stride 1,
+ * zero padding K/2; w [C][K], bias [C], eval-mode BatchNorm folded in by the caller), activation, bf16 output
+ * [n][L][C].  C in {16, 32, 64}, K odd <= 15.
+ * ocm_bias_act_bf16: Y[r][c] <- act(Y[r][c] + bias[c]) in place on a dense bf16 [rows][C] array, C a multiple of 8
+ * (the epilogue cuDNN does not fuse for ELU / GELU). */
+int ocm_vae_conv_in_bf16(const float* X, int64_t n, int32_t L, int64_t ldx, const float* spec_mean, const float* spec_std,
+                         const float* w, const float* bias, int32_t C, int32_t K, int32_t act, void* out_bf16, void* stream);
+int ocm_bias_act_bf16(void* Y_bf16, int64_t rows, int32_t C, const float* bias, int32_t act, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end call bench.py times as `e2e`) -------------
  * Scores h_X (HOST, pageable or pinned) in row chunks (chunk_rows <= 0: 65536), overlapping H2D copies with the
  * kernel on two internal streams, and writes h_T2 / h_Q / h_accept (HOST).  Synchronises before returning.  Its

@@ -738,6 +738,32 @@ def conformity_counts(accept, is_target):
     return counts
 
 
+ACTS = {"none": 0, "elu": 1, "gelu": 2}
+
+
+def vae_conv_in(x, spec_mean, spec_std, w, bias, act="elu"):
+    """First ConvVAE1D encoder block in one kernel (ocm_vae_conv_in_bf16): standardise fp32 rows x [n, L], Conv1d(1 -> C,
+    K taps, stride 1, 'same' zero padding) with w [C, K] / bias [C] (fp32, BatchNorm already folded in), activation;
+    returns bf16 [n, L, C] (channels-last)."""
+    torch = _torch()
+    n, L = x.shape
+    Cc, K = w.shape
+    out = torch.empty((n, L, Cc), dtype=torch.bfloat16, device=x.device)
+    rc = native.lib().ocm_vae_conv_in_bf16(_p(x), n, L, x.stride(0), _p(spec_mean), _p(spec_std), _p(w), _p(bias), Cc, K,
+                                           ACTS[act], _p(out), _stream())
+    native.check(rc, "ocm_vae_conv_in_bf16")
+    return out
+
+
+def bias_act_(y, bias, act="elu"):
+    """In place y[..., c] <- act(y[..., c] + bias[c]) on a dense bf16 tensor whose LAST (memory) axis is the channel
+    (ocm_bias_act_bf16)."""
+    Cc = y.shape[-1]
+    rc = native.lib().ocm_bias_act_bf16(_p(y), y.numel() // Cc, Cc, _p(bias), ACTS[act], _stream())
+    native.check(rc, "ocm_bias_act_bf16")
+    return y
+
+
 def latent_score(z=None, m=None, Sinv=None, x=None, xrec=None):
     """VAE-SIMCA epilogue: d2 = (z-m)^T Sinv (z-m), q = |x - xrec|^2 (ocm_latent_score_f32)."""
     torch = _torch()

@@ -162,16 +162,21 @@ def latent_recon_scores(vae, x, sample=False, recon_dtype=None):
 
 
 class FrozenScorer:
-    """Inference copy of a trained ConvVAE1D for the bulk scoring pass of config 5 (final_vaesimca.py:471-533): the
-    network stays PyTorch (cuDNN / cuBLAS), but as the scoring loop wants it -- eval-mode BatchNorm folded into the
-    convolutions, weights cast ONCE to `dtype` (no autocast casts per call), the 1-D convolutions run as 2-D ones
-    (H = 1) in channels-last memory format, which is the layout cuDNN's tensor-core kernels take without transposes.
+    """Inference copy of a trained ConvVAE1D for the bulk scoring pass of config 5 (final_vaesimca.py:471-533).  The
+    GEMM-shaped layers stay PyTorch's (cuDNN / cuBLAS), driven the way the scoring loop wants them -- eval-mode BatchNorm
+    folded into the convolutions, weights cast ONCE to `dtype` (no autocast casts per call), the 1-D convolutions run as
+    2-D ones (H = 1) on channels-last activations, the layout cuDNN's tensor-core kernels take without transposes -- and
+    the elementwise-bound rest is this library's (bf16 on CUDA, `fused=True`): the first block (standardise + 1-channel
+    convolution + activation) is one kernel (ocm_vae_conv_in_bf16), bias + ELU / GELU after every other convolution is
+    one in-place pass (ocm_bias_act_bf16) instead of torch's add_ + elu, and the two fully connected layers next to the
+    convolutions have their weights permuted once so that no activation tensor is ever transposed.
     Measured on a B200, batch 8192 x 1024: 4.4e5 spectra/s (autocast on the module) -> 5.5e5 (folded, bf16) -> 6.9e5
-    (+ channels-last).  `scorer(x)` returns (d2, q, mu) like `latent_recon_scores(vae, x, sample=False)`: deterministic
-    reconstruction dec(mu), one fused epilogue kernel (ocm_latent_score_f32).  The copy does not follow later
-    training of `vae`; build a new one after updating the weights or the calibration buffers."""
+    (+ channels-last) -> see DESIGN.md for the fused figure.  `scorer(x)` returns (d2, q, mu) like
+    `latent_recon_scores(vae, x, sample=False)`: deterministic reconstruction dec(mu), one fused epilogue kernel
+    (ocm_latent_score_f32).  The copy does not follow later training of `vae`; build a new one after updating the
+    weights or the calibration buffers."""
 
-    def __init__(self, vae, dtype=None):
+    def __init__(self, vae, dtype=None, fused=None):
         import copy
         import torch
         from torch import nn
@@ -180,54 +185,116 @@ class FrozenScorer:
             dtype = torch.bfloat16
         src = copy.deepcopy(vae).eval()
         dev = src.spec_mean.device
+        act_name = lambda m: "elu" if isinstance(m, nn.ELU) and m.alpha == 1.0 else \
+            "gelu" if isinstance(m, nn.GELU) and getattr(m, "approximate", "none") == "none" else None
 
-        def rebuild(seq):
+        def blocks_of(seq):
+            """[(folded fp32 conv module, 'elu' | 'gelu' | None | activation module)] of a conv Sequential."""
             mods, out, i = list(seq), [], 0
             while i < len(mods):
                 m = mods[i]
                 if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
-                    tr = isinstance(m, nn.ConvTranspose1d)
                     if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
-                        m = fuse_conv_bn_eval(m, mods[i + 1], transpose=tr)
+                        m = fuse_conv_bn_eval(m, mods[i + 1], transpose=isinstance(m, nn.ConvTranspose1d))
                         i += 1
-                    kw = dict(stride=(1, m.stride[0]), padding=(0, m.padding[0]))
-                    if tr:
-                        c = nn.ConvTranspose2d(m.in_channels, m.out_channels, (1, m.kernel_size[0]),
-                                               output_padding=(0, m.output_padding[0]), **kw)
-                    else:
-                        c = nn.Conv2d(m.in_channels, m.out_channels, (1, m.kernel_size[0]), **kw)
-                    c.weight.data = m.weight.data.unsqueeze(2).clone()
-                    c.bias.data = m.bias.data.clone() if m.bias is not None else torch.zeros_like(c.bias.data)
-                    out.append(c)
-                elif isinstance(m, nn.Dropout):
-                    pass                                  # identity in eval mode
-                else:
-                    out.append(m)
+                    act = None
+                    if i + 1 < len(mods) and not isinstance(mods[i + 1], (nn.Conv1d, nn.ConvTranspose1d, nn.BatchNorm1d, nn.Dropout)):
+                        act = act_name(mods[i + 1]) or mods[i + 1]
+                        i += 1
+                    out.append((m, act))
+                elif not isinstance(m, nn.Dropout):               # dropout is the identity in eval mode
+                    raise ValueError(f"unexpected layer in a ConvVAE1D conv stack: {type(m).__name__}")
                 i += 1
-            return nn.Sequential(*out).to(device=dev, dtype=dtype).to(memory_format=torch.channels_last).eval()
+            return out
 
+        enc, dec = blocks_of(src.encoder_conv), blocks_of(src.decoder_conv)
         self.dtype = dtype
-        self.enc, self.dec = rebuild(src.encoder_conv), rebuild(src.decoder_conv)
-        self.fc, self.fc_mu, self.fc_dec = src.fc.to(dtype), src.fc_mu.to(dtype), src.fc_dec.to(dtype)
         self.L, self.C, self.Lenc = src.input_length, src._enc_out_channels, src._enc_out_length
-        self.spec_mean, self.spec_std = src.spec_mean.float(), src.spec_std.float()
+        self.spec_mean, self.spec_std = src.spec_mean.float().contiguous(), src.spec_std.float().contiguous()
         self.mean_d, self.std_d = self.spec_mean.to(dtype), self.spec_std.to(dtype)
         self.latent_mean, self.latent_cov_inv = src.latent_mean.float(), src.latent_cov_inv.float()
+        c0 = enc[0][0]
+        can_fuse = (dtype == torch.bfloat16 and dev.type == "cuda"
+                    and all(isinstance(a, str) or a is None for _, a in enc + dec)
+                    and all(c.out_channels % 8 == 0 for c, a in enc + dec if a is not None)
+                    and isinstance(c0, nn.Conv1d) and c0.in_channels == 1 and c0.stride[0] == 1 and c0.kernel_size[0] % 2 == 1
+                    and c0.kernel_size[0] <= 15 and c0.padding[0] == c0.kernel_size[0] // 2 and c0.out_channels in (16, 32, 64)
+                    and isinstance(enc[0][1], str))
+        self.fused = can_fuse if fused is None else bool(fused)
+        if self.fused and not can_fuse:
+            raise ValueError("this network / dtype / device cannot take the fused scoring path")
+
+        def layer(m, act):
+            """(kind, weight [Cout|Cin, ., 1, K] in `dtype` channels-last, fp32 bias, conv kwargs, activation)"""
+            tr = isinstance(m, nn.ConvTranspose1d)
+            kw = dict(stride=(1, m.stride[0]), padding=(0, m.padding[0]))
+            if tr:
+                kw["output_padding"] = (0, m.output_padding[0])
+            w = m.weight.data.unsqueeze(2).to(device=dev, dtype=dtype).contiguous(memory_format=torch.channels_last)
+            b = (m.bias.data if m.bias is not None else torch.zeros(m.out_channels)).to(device=dev, dtype=torch.float32).contiguous()
+            return ("convT" if tr else "conv", w, b, kw, act)
+
+        self.enc, self.dec = [layer(m, a) for m, a in enc], [layer(m, a) for m, a in dec]
+        if self.fused:
+            self.w_in = c0.weight.data.reshape(c0.out_channels, -1).to(device=dev, dtype=torch.float32).contiguous()
+        # fully connected layers next to the convolutions: columns / rows permuted once from the module's (c, l) order to
+        # the (l, c) order the channels-last activations have in memory
+        self.fc, self.fc_mu, self.fc_dec = src.fc.to(dtype), src.fc_mu.to(dtype), src.fc_dec.to(dtype)
+        lin_in = self.fc[0]
+        lin_out = [m for m in self.fc_dec if isinstance(m, nn.Linear)][-1]
+        C, Le = self.C, self.Lenc
+        with torch.no_grad():
+            lin_in.weight.copy_(lin_in.weight.view(-1, C, Le).permute(0, 2, 1).reshape(-1, C * Le).clone())
+            lin_out.weight.copy_(lin_out.weight.view(C, Le, -1).permute(1, 0, 2).reshape(C * Le, -1).clone())
+            lin_out.bias.copy_(lin_out.bias.view(C, Le).t().reshape(-1).clone())
+
+    @staticmethod
+    def _dense_nlc(y):
+        """logical [n, C, 1, L] -> (same tensor, its [n, 1, L, C] memory view), made dense channels-last if it is not"""
+        ym = y.permute(0, 2, 3, 1)
+        if not ym.is_contiguous():
+            ym = ym.contiguous()
+            y = ym.permute(0, 3, 1, 2)
+        return y, ym
+
+    def _stack(self, layers, h):
+        import torch
+        import torch.nn.functional as F
+        for kind, w, b, kw, act in layers:
+            f = F.conv_transpose2d if kind == "convT" else F.conv2d
+            if self.fused and act is not None:
+                h, hm = self._dense_nlc(f(h, w, None, **kw))
+                engine.bias_act_(hm, b, act)
+            else:
+                h = f(h, w, b.to(self.dtype), **kw)
+                if act is not None:
+                    h = (torch.nn.functional.elu(h) if act == "elu" else torch.nn.functional.gelu(h)) if isinstance(act, str) else act(h)
+        return h
 
     def encode_decode(self, x):
         """(mu [n, d], x_rec [n, L]) in the scorer's dtype for fp32 rows x."""
         import torch
         with torch.no_grad():
-            xs = ((x - self.spec_mean) / self.spec_std).to(self.dtype)
-            h = self.enc(xs.view(-1, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
-            mu = self.fc_mu(self.fc(h.squeeze(2).flatten(1)))         # logical [n, C, L'] order, as `fc` was trained on
-            g = self.fc_dec(mu).view(-1, self.C, 1, self.Lenc).contiguous(memory_format=torch.channels_last)
-            xr = self.dec(g).reshape(x.shape[0], -1)
-            n = xr.shape[1]
-            if n > self.L:
+            n = x.shape[0]
+            if self.fused:
+                x = x.float()
+                if x.stride(1) != 1:
+                    x = x.contiguous()
+                kind, w, b, kw, act = self.enc[0]
+                h = engine.vae_conv_in(x, self.spec_mean, self.spec_std, self.w_in, b, act)      # [n, L, C0] bf16
+                h = self._stack(self.enc[1:], h.view(n, 1, self.L, -1).permute(0, 3, 1, 2))
+            else:
+                xs = ((x - self.spec_mean) / self.spec_std).to(self.dtype)
+                h = self._stack(self.enc, xs.view(n, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
+            _, hm = self._dense_nlc(h)
+            mu = self.fc_mu(self.fc(hm.reshape(n, -1)))                  # (l, c) order: `fc` was permuted to match
+            g = self.fc_dec(mu).view(n, 1, self.Lenc, self.C).permute(0, 3, 1, 2)      # logical [n, C, 1, L'], channels-last memory
+            xr = self._stack(self.dec, g).reshape(n, -1)
+            m = xr.shape[1]
+            if m > self.L:
                 xr = xr[:, : self.L]
-            elif n < self.L:
-                xr = torch.nn.functional.pad(xr, (0, self.L - n))
+            elif m < self.L:
+                xr = torch.nn.functional.pad(xr, (0, self.L - m))
             return mu, (xr * self.std_d + self.mean_d).contiguous()
 
     def __call__(self, x):

@@ -1087,9 +1087,41 @@ def test_frozen_scorer_matches_the_module_path(torch):
     np.testing.assert_allclose(d2.cpu().numpy(), d2r.cpu().numpy(), rtol=5e-3, atol=1e-3)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         d2a, qa, _ = latent_recon_scores(vae, X, sample=False, recon_dtype=torch.bfloat16)
-    d2b, qb, _ = FrozenScorer(vae)(X)
-    assert float(((qb - qa).abs() / qa).median()) < 2e-2 and float(((qb - qr).abs() / qr).median()) < 5e-2
-    assert float(((d2b - d2a).abs() / (d2a + 1e-3)).median()) < 5e-2
+    fused, plain = FrozenScorer(vae), FrozenScorer(vae, fused=False)
+    assert fused.fused and not plain.fused
+    l0 = native.launch_count()
+    d2b, qb, mub = fused(X)
+    assert native.launch_count() - l0 == 1 + 5 + 1      # first block, bias + activation after five convolutions, epilogue
+    d2p, qp, mup = plain(X)
+    for qx, d2x in ((qb, d2b), (qp, d2p)):
+        assert float(((qx - qa).abs() / qa).median()) < 2e-2 and float(((qx - qr).abs() / qr).median()) < 5e-2
+        assert float(((d2x - d2a).abs() / (d2a + 1e-3)).median()) < 5e-2
+    assert float(((qb - qp).abs() / qp).median()) < 1e-2 and float((mub.float() - mup.float()).abs().median()) < 2e-2
+
+
+def test_vae_layer_kernels(torch):
+    """ocm_vae_conv_in_bf16 (standardise + 1-channel convolution + folded bias + activation, channels-last bf16) and
+    ocm_bias_act_bf16 (in-place bias + activation) against the same arithmetic in torch fp32."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    for n, L, Cc, K, act in ((37, 1024, 32, 9, "elu"), (5, 700, 16, 5, "gelu"), (3, 333, 64, 15, "none"), (2, 64, 32, 1, "elu")):
+        x = torch.randn(n, L, device=dev, generator=g) * 0.3 + 1.0
+        mean = torch.full((L,), 1.0, device=dev) + 0.01 * torch.randn(L, device=dev, generator=g)
+        std = 0.3 + 0.05 * torch.rand(L, device=dev, generator=g)
+        w = torch.randn(Cc, K, device=dev, generator=g) / K ** 0.5
+        b = torch.randn(Cc, device=dev, generator=g) * 0.1
+        out = engine.vae_conv_in(x, mean, std, w, b, act)
+        ref = F.conv1d(((x - mean) / std).unsqueeze(1), w.unsqueeze(1), b, padding=K // 2)      # [n, C, L]
+        ref = {"elu": F.elu, "gelu": F.gelu, "none": lambda t: t}[act](ref).permute(0, 2, 1)
+        assert out.shape == (n, L, Cc) and out.dtype == torch.bfloat16
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2, err_msg=f"{n} {L} {Cc} {K} {act}")
+    for rows, Cc, act in ((1000, 64, "elu"), (77, 8, "gelu"), (4096 * 33, 32, "elu"), (5, 128, "none")):
+        y = (torch.randn(rows, Cc, device=dev, generator=g) * 2).to(torch.bfloat16)
+        b = torch.randn(Cc, device=dev, generator=g)
+        ref = {"elu": F.elu, "gelu": F.gelu, "none": lambda t: t}[act](y.float() + b).to(torch.bfloat16)
+        got = engine.bias_act_(y.clone(), b, act)
+        np.testing.assert_allclose(got.float().cpu().numpy(), ref.float().cpu().numpy(), rtol=8e-3, atol=1e-3, err_msg=f"{rows} {Cc} {act}")
 
 
 def test_smoke_entry(torch):
