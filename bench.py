@@ -534,8 +534,9 @@ def vae_leg(args, device, group, rank, world, local_rank):
     return {"metric": "VAE-SIMCA spectra/s (ConvVAE1D latent 16, bf16)", "n_gpus": world, "rows_total": rows_total, "rows_per_gpu": n,
             "scaling": "strong (1 M rows in total, sharded)",
             "scoring": {"value": rows_total / (score_ms * 1e-3), "unit": "spectra/s", "ms_per_pass": score_ms, "batch": Bs,
-                        "what": "bf16 encoder + decoder (PyTorch cuDNN/cuBLAS; vae.FrozenScorer: BatchNorm folded, weights cast once, channels-last "
-                                "2-D convolutions) + fused latent T2 / reconstruction Q kernel, whole shard",
+                        "what": "bf16 encoder + decoder through vae.FrozenScorer (GEMM-shaped layers: PyTorch cuDNN/cuBLAS on channels-last "
+                                "activations, BatchNorm folded, weights cast once; first block and every bias + activation: kernels of "
+                                "this library) + fused latent T2 / reconstruction Q kernel, whole shard",
                         "gpu_launches": int(launches), "accepted_frac_p95_rule": acc_frac},
             "training": {"value": world * Bt / (train_ms * 1e-3), "unit": "spectra/s", "ms_per_step": train_ms, "batch_per_gpu": Bt,
                          "what": "DistributedDataParallel bf16-autocast step (fwd + bwd + NCCL gradient all-reduce + fused Adam), channels-last execution" if world > 1

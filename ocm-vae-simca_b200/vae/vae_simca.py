@@ -247,6 +247,16 @@ class FrozenScorer:
             lin_in.weight.copy_(lin_in.weight.view(-1, C, Le).permute(0, 2, 1).reshape(-1, C * Le).clone())
             lin_out.weight.copy_(lin_out.weight.view(C, Le, -1).permute(1, 0, 2).reshape(C * Le, -1).clone())
             lin_out.bias.copy_(lin_out.bias.view(C, Le).t().reshape(-1).clone())
+        # fused path: fc_dec = head (everything before its last Linear) + (last Linear, its bias per (l, c) entry, activation)
+        self.fc_dec_tail = None
+        mods = list(self.fc_dec)
+        k = max(i for i, m in enumerate(mods) if isinstance(m, nn.Linear))
+        tail_act = [act_name(m) for m in mods[k + 1:] if not isinstance(m, (nn.Identity, nn.Dropout))]
+        if self.fused and len(tail_act) == 1 and tail_act[0] is not None and C % 8 == 0:
+            # bias_act_ broadcasts bias[c] over rows of C entries; this bias differs per (l, c): keep it as one row of
+            # L' C entries, i.e. call the kernel with "C" = L' C on [n, L' C]
+            self.fc_dec_head = nn.Sequential(*mods[:k])
+            self.fc_dec_tail = (lin_out, lin_out.bias.data.float().contiguous(), tail_act[0])
 
     @staticmethod
     def _dense_nlc(y):
@@ -288,7 +298,14 @@ class FrozenScorer:
                 h = self._stack(self.enc, xs.view(n, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
             _, hm = self._dense_nlc(h)
             mu = self.fc_mu(self.fc(hm.reshape(n, -1)))                  # (l, c) order: `fc` was permuted to match
-            g = self.fc_dec(mu).view(n, 1, self.Lenc, self.C).permute(0, 3, 1, 2)      # logical [n, C, 1, L'], channels-last memory
+            if self.fused and self.fc_dec_tail is not None:
+                # the wide last layer of fc_dec (hidden -> C L'): GEMM without bias, then bias + activation in one pass
+                lin, bias32, act = self.fc_dec_tail
+                g = torch.nn.functional.linear(self.fc_dec_head(mu), lin.weight)
+                engine.bias_act_(g, bias32, act)                         # one "row" of L' C biases per spectrum
+            else:
+                g = self.fc_dec(mu)
+            g = g.view(n, 1, self.Lenc, self.C).permute(0, 3, 1, 2)      # logical [n, C, 1, L'], channels-last memory
             xr = self._stack(self.dec, g).reshape(n, -1)
             m = xr.shape[1]
             if m > self.L:

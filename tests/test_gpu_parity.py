@@ -1091,7 +1091,7 @@ def test_frozen_scorer_matches_the_module_path(torch):
     assert fused.fused and not plain.fused
     l0 = native.launch_count()
     d2b, qb, mub = fused(X)
-    assert native.launch_count() - l0 == 1 + 5 + 1      # first block, bias + activation after five convolutions, epilogue
+    assert native.launch_count() - l0 == 1 + 5 + 1 + 1      # first block, bias + activation after five convolutions and after fc_dec, epilogue
     d2p, qp, mup = plain(X)
     for qx, d2x in ((qb, d2b), (qp, d2p)):
         assert float(((qx - qa).abs() / qa).median()) < 2e-2 and float(((qx - qr).abs() / qr).median()) < 5e-2
