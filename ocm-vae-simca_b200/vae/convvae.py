@@ -112,6 +112,10 @@ class ConvVAE1D(nn.Module):
                                         output_padding=(0, m.output_padding[0]))
             elif isinstance(m, nn.Conv1d):
                 x4 = F.conv2d(x4, m.weight.unsqueeze(2), m.bias, stride=(1, m.stride[0]), padding=(0, m.padding[0]))
+                if m.in_channels == 1 and not x4.is_contiguous(memory_format=torch.channels_last):
+                    # a 1-channel input has no memory format of its own, so cuDNN answers in NCHW and every later layer
+                    # (BatchNorm's generic kernels included) would follow: convert once, here
+                    x4 = x4.contiguous(memory_format=torch.channels_last)
             elif isinstance(m, nn.BatchNorm1d):
                 if m.training and m.track_running_stats and m.num_batches_tracked is not None:
                     m.num_batches_tracked.add_(1)

@@ -40,7 +40,12 @@ def forward_cl(vae, x):
     return xr * vae.spec_std + vae.spec_mean, mu, logvar
 
 
-for name, fwd in (("module", lambda v, x: v(x)), ("channels_last_2d", forward_cl)):
+def fwd_flag(v, x):
+    v.channels_last = True
+    return v(x)
+
+
+for name, fwd in (("module", lambda v, x: v(x)), ("channels_last_2d (script)", forward_cl), ("ConvVAE1D.channels_last", fwd_flag)):
     torch.manual_seed(0)
     vae = ConvVAE1D(L, d, mean.cpu().numpy(), std.cpu().numpy()).to(dev).train()
     opt = torch.optim.Adam(vae.parameters(), lr=1e-4, fused=True)
