@@ -299,6 +299,13 @@ int ocm_latent_score_f32(const float* z, int64_t n, int32_t d, int64_t ldz,
 int ocm_vae_conv_in_bf16(const float* X, int64_t n, int32_t L, int64_t ldx, const float* spec_mean, const float* spec_std,
                          const float* w, const float* bias, int32_t C, int32_t K, int32_t act, void* out_bf16, void* stream);
 int ocm_bias_act_bf16(void* Y_bf16, int64_t rows, int32_t C, const float* bias, int32_t act, void* stream);
+/* Tail of the decoder in one pass (vae_model.py:95-129 + the reconstruction Q of final_vaesimca.py:484-492): Y [n][Ly][C]
+ * bf16 = raw output of the last transposed convolution; a = act(Y + bias), s = sum_c a_c w_out[c] + b_out (the 1x1 output
+ * convolution), x_rec_l = s spec_std_l + spec_mean_l (l >= Ly: s = 0), q = sum_{l < L} (X_l - x_rec_l)^2.  xrec_bf16
+ * [n][L] may be NULL.  C in {16, 32, 64}. */
+int ocm_vae_tail_q_bf16(const void* Y_bf16, int64_t n, int32_t Ly, int32_t C, const float* bias, int32_t act,
+                        const float* w_out, float b_out, const float* X, int64_t ldx, int32_t L,
+                        const float* spec_mean, const float* spec_std, float* q, void* xrec_bf16, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end call bench.py times as `e2e`) -------------
  * Scores h_X (HOST, pageable or pinned) in row chunks (chunk_rows <= 0: 65536), overlapping H2D copies with the

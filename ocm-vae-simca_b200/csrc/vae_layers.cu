@@ -99,8 +99,76 @@ bias_act_bf16_kernel(__nv_bfloat16* __restrict__ Y, int64_t chunks, int C, const
     }
 }
 
+// Tail of the decoder in one pass: y [n][Ly][C] is the LAST transposed convolution's raw output (bias not yet added);
+// a = act(y + bias), s = sum_c a_c w_out[c] + b_out (the 1x1 output convolution), x_rec = s std_l + mean_l (positions
+// l >= Ly: s = 0, what F.pad gives), q = sum_l (x_l - x_rec_l)^2.  Neither the activated tensor nor the reconstruction
+// goes back to HBM (x_rec optionally, as bf16).  One warp per spectrum, a lane per position: 2 C bytes each, contiguous.
+template <int C>
+__global__ void __launch_bounds__(256)
+vae_tail_q_kernel(const __nv_bfloat16* __restrict__ Y, int64_t n, int Ly, const float* __restrict__ bias, int act,
+                  const float* __restrict__ w_out, float b_out, const float* __restrict__ X, int64_t ldx, int L,
+                  const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ q,
+                  __nv_bfloat16* __restrict__ xrec) {
+    __shared__ __align__(16) float s_b[C], s_w[C];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_b[i] = bias[i]; s_w[i] = w_out[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = wid; row < n; row += nw) {
+        float acc = 0.f;
+        for (int l = lane; l < L; l += 32) {
+            float s = 0.f;
+            if (l < Ly) {
+                const uint4* yp = reinterpret_cast<const uint4*>(Y + (row * Ly + l) * C);
+                s = b_out;
+#pragma unroll
+                for (int c8 = 0; c8 < C / 8; ++c8) {
+                    const uint4 v = yp[c8];
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 8 * c8 + 2 * k;
+                        s = fmaf(activate(__low2float(h[k]) + s_b[c], act), s_w[c], s);
+                        s = fmaf(activate(__high2float(h[k]) + s_b[c + 1], act), s_w[c + 1], s);
+                    }
+                }
+            }
+            const float xr = fmaf(s, stdv[l], mean[l]);
+            if (xrec) xrec[row * L + l] = __float2bfloat16(xr);
+            const float e = X[row * ldx + l] - xr;
+            acc = fmaf(e, e, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) q[row] = acc;
+    }
+}
+
 }  // namespace vae
 }  // namespace ocm
+
+extern "C" int ocm_vae_tail_q_bf16(const void* Y, int64_t n, int32_t Ly, int32_t C, const float* bias, int32_t act,
+                                   const float* w_out, float b_out, const float* X, int64_t ldx, int32_t L,
+                                   const float* spec_mean, const float* spec_std, float* q, void* xrec, void* stream) {
+    using namespace ocm;
+    using namespace ocm::vae;
+    if (n == 0) return 0;
+    OCM_REQUIRE(Y && bias && w_out && X && spec_mean && spec_std && q && n > 0 && Ly > 0 && L > 0 && ldx >= L, OCM_EINVAL,
+                "bad shape or NULL buffer");
+    OCM_REQUIRE(C == 16 || C == 32 || C == 64, OCM_ELIMIT, "last block: 16 / 32 / 64 filters");
+    OCM_REQUIRE(act >= ACT_NONE && act <= ACT_GELU, OCM_EINVAL, "unknown activation");
+    OCM_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, OCM_EALIGN, "Y must be 16-byte aligned");
+    int64_t blocks = (n + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* y = static_cast<const __nv_bfloat16*>(Y);
+    __nv_bfloat16* xr = static_cast<__nv_bfloat16*>(xrec);
+#define OCM_TAIL(C_) vae_tail_q_kernel<C_><<<(unsigned)blocks, 256, 0, st>>>(y, n, Ly, bias, act, w_out, b_out, X, ldx, L, spec_mean, spec_std, q, xr)
+    if (C == 16) OCM_TAIL(16); else if (C == 32) OCM_TAIL(32); else OCM_TAIL(64);
+#undef OCM_TAIL
+    return check_launch("vae_tail_q_kernel");
+}
 
 extern "C" int ocm_vae_conv_in_bf16(const float* X, int64_t n, int32_t L, int64_t ldx, const float* spec_mean,
                                     const float* spec_std, const float* w, const float* bias, int32_t C, int32_t K,

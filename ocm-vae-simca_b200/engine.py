@@ -764,6 +764,20 @@ def bias_act_(y, bias, act="elu"):
     return y
 
 
+def vae_tail_q(y, bias, act, w_out, b_out, x, spec_mean, spec_std, want_xrec=False):
+    """Decoder tail + reconstruction Q in one kernel (ocm_vae_tail_q_bf16): y [n, Ly, C] bf16 (raw output of the last
+    transposed convolution, channels-last), x [n, L] fp32.  Returns q [n] fp32 (and x_rec [n, L] bf16 when asked)."""
+    torch = _torch()
+    n, Ly, Cc = y.shape
+    L = x.shape[1]
+    q = torch.empty(n, dtype=torch.float32, device=x.device)
+    xr = torch.empty((n, L), dtype=torch.bfloat16, device=x.device) if want_xrec else None
+    rc = native.lib().ocm_vae_tail_q_bf16(_p(y), n, Ly, Cc, _p(bias), ACTS[act], _p(w_out), float(b_out), _p(x), x.stride(0), L,
+                                          _p(spec_mean), _p(spec_std), _p(q), _p(xr), _stream())
+    native.check(rc, "ocm_vae_tail_q_bf16")
+    return (q, xr) if want_xrec else q
+
+
 def latent_score(z=None, m=None, Sinv=None, x=None, xrec=None):
     """VAE-SIMCA epilogue: d2 = (z-m)^T Sinv (z-m), q = |x - xrec|^2 (ocm_latent_score_f32)."""
     torch = _torch()

@@ -147,6 +147,7 @@ SIGNATURES = {
                                            _vp, _vp, _vp]),
     "ocm_vae_conv_in_bf16": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ocm_bias_act_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp]),
+    "ocm_vae_tail_q_bf16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _f32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ocm_upload_rows": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64]),
     "ocm_simca_score_host_f64in": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams), _i64,
                                              _vp, _vp, _vp]),

@@ -235,8 +235,16 @@ class FrozenScorer:
             return ("convT" if tr else "conv", w, b, kw, act)
 
         self.enc, self.dec = [layer(m, a) for m, a in enc], [layer(m, a) for m, a in dec]
+        self.tail = None
         if self.fused:
             self.w_in = c0.weight.data.reshape(c0.out_channels, -1).to(device=dev, dtype=torch.float32).contiguous()
+            # decoder tail: [..., (transposed) convolution + activation, 1x1 convolution to one channel] -> one kernel
+            if len(dec) >= 2:
+                (cl, al), (co, ao) = dec[-2], dec[-1]
+                if (isinstance(al, str) and ao is None and isinstance(co, nn.Conv1d) and co.out_channels == 1 and co.kernel_size[0] == 1
+                        and co.stride[0] == 1 and co.padding[0] == 0 and cl.out_channels in (16, 32, 64)):
+                    self.tail = (co.weight.data.reshape(-1).to(device=dev, dtype=torch.float32).contiguous(),
+                                 float(co.bias.data) if co.bias is not None else 0.0)
         # fully connected layers next to the convolutions: columns / rows permuted once from the module's (c, l) order to
         # the (l, c) order the channels-last activations have in memory
         self.fc, self.fc_mu, self.fc_dec = src.fc.to(dtype), src.fc_mu.to(dtype), src.fc_dec.to(dtype)
@@ -281,31 +289,40 @@ class FrozenScorer:
                     h = (torch.nn.functional.elu(h) if act == "elu" else torch.nn.functional.gelu(h)) if isinstance(act, str) else act(h)
         return h
 
+    def _encode(self, x):
+        """mu [n, d] and the decoder's input g (logical [n, C, 1, L'], channels-last memory) for fp32 rows x"""
+        import torch
+        n = x.shape[0]
+        if self.fused:
+            kind, w, b, kw, act = self.enc[0]
+            h = engine.vae_conv_in(x, self.spec_mean, self.spec_std, self.w_in, b, act)      # [n, L, C0] bf16
+            h = self._stack(self.enc[1:], h.view(n, 1, self.L, -1).permute(0, 3, 1, 2))
+        else:
+            xs = ((x - self.spec_mean) / self.spec_std).to(self.dtype)
+            h = self._stack(self.enc, xs.view(n, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
+        _, hm = self._dense_nlc(h)
+        mu = self.fc_mu(self.fc(hm.reshape(n, -1)))                  # (l, c) order: `fc` was permuted to match
+        if self.fused and self.fc_dec_tail is not None:
+            # the wide last layer of fc_dec (hidden -> C L'): GEMM without bias, then bias + activation in one pass
+            lin, bias32, act = self.fc_dec_tail
+            g = torch.nn.functional.linear(self.fc_dec_head(mu), lin.weight)
+            engine.bias_act_(g, bias32, act)                         # one "row" of L' C biases per spectrum
+        else:
+            g = self.fc_dec(mu)
+        return mu, g.view(n, 1, self.Lenc, self.C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def _as_rows(x):
+        x = x.float()
+        return x if x.stride(1) == 1 else x.contiguous()
+
     def encode_decode(self, x):
         """(mu [n, d], x_rec [n, L]) in the scorer's dtype for fp32 rows x."""
         import torch
         with torch.no_grad():
+            x = self._as_rows(x)
             n = x.shape[0]
-            if self.fused:
-                x = x.float()
-                if x.stride(1) != 1:
-                    x = x.contiguous()
-                kind, w, b, kw, act = self.enc[0]
-                h = engine.vae_conv_in(x, self.spec_mean, self.spec_std, self.w_in, b, act)      # [n, L, C0] bf16
-                h = self._stack(self.enc[1:], h.view(n, 1, self.L, -1).permute(0, 3, 1, 2))
-            else:
-                xs = ((x - self.spec_mean) / self.spec_std).to(self.dtype)
-                h = self._stack(self.enc, xs.view(n, 1, 1, self.L).contiguous(memory_format=torch.channels_last))
-            _, hm = self._dense_nlc(h)
-            mu = self.fc_mu(self.fc(hm.reshape(n, -1)))                  # (l, c) order: `fc` was permuted to match
-            if self.fused and self.fc_dec_tail is not None:
-                # the wide last layer of fc_dec (hidden -> C L'): GEMM without bias, then bias + activation in one pass
-                lin, bias32, act = self.fc_dec_tail
-                g = torch.nn.functional.linear(self.fc_dec_head(mu), lin.weight)
-                engine.bias_act_(g, bias32, act)                         # one "row" of L' C biases per spectrum
-            else:
-                g = self.fc_dec(mu)
-            g = g.view(n, 1, self.Lenc, self.C).permute(0, 3, 1, 2)      # logical [n, C, 1, L'], channels-last memory
+            mu, g = self._encode(x)
             xr = self._stack(self.dec, g).reshape(n, -1)
             m = xr.shape[1]
             if m > self.L:
@@ -315,9 +332,25 @@ class FrozenScorer:
             return mu, (xr * self.std_d + self.mean_d).contiguous()
 
     def __call__(self, x):
-        mu, xr = self.encode_decode(x)
-        d2, q = engine.latent_score(z=mu.float(), m=self.latent_mean, Sinv=self.latent_cov_inv, x=x.float(), xrec=xr)
-        return d2, q, mu
+        import torch
+        import torch.nn.functional as F
+        if not (self.fused and self.tail is not None):
+            mu, xr = self.encode_decode(x)
+            d2, q = engine.latent_score(z=mu.float(), m=self.latent_mean, Sinv=self.latent_cov_inv, x=x.float(), xrec=xr)
+            return d2, q, mu
+        # fused tail: the last transposed convolution's raw output goes straight into one kernel that adds the bias,
+        # activates, applies the 1x1 output convolution, de-standardises and reduces q -- the reconstruction is never stored
+        with torch.no_grad():
+            x = self._as_rows(x)
+            n = x.shape[0]
+            mu, g = self._encode(x)
+            h = self._stack(self.dec[:-2], g)
+            kind, w, b, kw, act = self.dec[-2]
+            _, ym = self._dense_nlc((F.conv_transpose2d if kind == "convT" else F.conv2d)(h, w, None, **kw))
+            w_out, b_out = self.tail
+            q = engine.vae_tail_q(ym.view(n, ym.shape[2], ym.shape[3]), b, act, w_out, b_out, x, self.spec_mean, self.spec_std)
+            d2, _ = engine.latent_score(z=mu.float(), m=self.latent_mean, Sinv=self.latent_cov_inv)
+            return d2, q, mu
 
 
 def compute_q_h_f(x, x_rec, z):

@@ -1091,7 +1091,8 @@ def test_frozen_scorer_matches_the_module_path(torch):
     assert fused.fused and not plain.fused
     l0 = native.launch_count()
     d2b, qb, mub = fused(X)
-    assert native.launch_count() - l0 == 1 + 5 + 1 + 1      # first block, bias + activation after five convolutions and after fc_dec, epilogue
+    # first block; bias + activation after four convolutions and after fc_dec; decoder tail + q; latent d2
+    assert fused.tail is not None and native.launch_count() - l0 == 1 + 4 + 1 + 1 + 1
     d2p, qp, mup = plain(X)
     for qx, d2x in ((qb, d2b), (qp, d2p)):
         assert float(((qx - qa).abs() / qa).median()) < 2e-2 and float(((qx - qr).abs() / qr).median()) < 5e-2
@@ -1116,6 +1117,21 @@ def test_vae_layer_kernels(torch):
         ref = {"elu": F.elu, "gelu": F.gelu, "none": lambda t: t}[act](ref).permute(0, 2, 1)
         assert out.shape == (n, L, Cc) and out.dtype == torch.bfloat16
         np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2, err_msg=f"{n} {L} {Cc} {K} {act}")
+    # decoder tail: bias + activation + 1x1 output convolution + de-standardisation + q in one kernel
+    for n, Ly, L, Cc, act in ((50, 1024, 1024, 32, "elu"), (7, 704, 700, 16, "gelu"), (3, 120, 131, 64, "elu")):
+        y = torch.randn(n, Ly, Cc, device=dev, generator=g).to(torch.bfloat16)
+        b = torch.randn(Cc, device=dev, generator=g) * 0.2
+        wo = torch.randn(Cc, device=dev, generator=g) / Cc ** 0.5
+        bo = 0.123
+        x = torch.randn(n, L, device=dev, generator=g)
+        mean = torch.randn(L, device=dev, generator=g) * 0.1; std = 0.5 + torch.rand(L, device=dev, generator=g)
+        q, xr = engine.vae_tail_q(y, b, act, wo, bo, x, mean, std, want_xrec=True)
+        a = {"elu": F.elu, "gelu": F.gelu}[act](y.float() + b)
+        s_ = a @ wo + bo                                                        # [n, Ly]
+        s_ = s_[:, :L] if Ly >= L else F.pad(s_, (0, L - Ly))
+        xr_ref = s_ * std + mean
+        np.testing.assert_allclose(xr.float().cpu().numpy(), xr_ref.cpu().numpy(), rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(q.cpu().numpy(), (x - xr_ref).pow(2).sum(1).cpu().numpy(), rtol=2e-4)
     for rows, Cc, act in ((1000, 64, "elu"), (77, 8, "gelu"), (4096 * 33, 32, "elu"), (5, 128, "none")):
         y = (torch.randn(rows, Cc, device=dev, generator=g) * 2).to(torch.bfloat16)
         b = torch.randn(Cc, device=dev, generator=g)
