@@ -1,5 +1,5 @@
 """Launch every hot kernel of the library a few times on representative shapes (for ncu: `-k regex:...` picks one).
-usage: python tools/kernels_once.py [score|gram|f64|all]"""
+usage: python tools/kernels_once.py [score|gram|f64|vae|all]"""
 import sys
 import numpy as np
 import torch
@@ -64,5 +64,15 @@ if what == "f64":
     Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
     for snv in (False, False, True):
         engine.score(X, pca.mean, pca.P, Sinv, rule="alt", ct=0.05, cq=100.0, x_rms=pca.x_rms, snv=snv)
+    torch.cuda.synchronize()
+if what == "vae":
+    # config-5 scoring pass through vae.FrozenScorer: first block, bias + activation, decoder tail (csrc/vae_layers.cu)
+    from ocm_vae_simca_b200.vae import ConvVAE1D, FrozenScorer
+    X = synth.make_spectra_device(16384, 1024, dev, seed=9)
+    torch.manual_seed(0)
+    vae = ConvVAE1D(1024, 16, X.mean(0).cpu().numpy(), (X.std(0) + 1e-8).cpu().numpy()).to(dev).eval()
+    sc = FrozenScorer(vae)
+    for r in (0, 8192, 0):
+        sc(X[r:r + 8192])
     torch.cuda.synchronize()
 print("ok")
