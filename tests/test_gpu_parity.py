@@ -402,6 +402,31 @@ def test_subspace_eigensolver_kernels(torch):
             np.testing.assert_allclose(tails[f].cpu().numpy(), [rest.sum(), (rest ** 2).sum(), (rest ** 3).sum()], rtol=1e-9)
 
 
+def test_subspace_iteration_graph_replay_equals_eager(torch):
+    """The subspace-iteration cycle replayed from its CUDA graph (engine._eig_graph) gives bit for bit what the eager
+    loop gives: batched (CV-fold shape) and single (fit shape), repeated calls on the cached graph included."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    for F, p, k in ((4, 260, 20), (1, 512, 10)):
+        B = torch.randn(F, p, 40, device=dev, dtype=torch.float64, generator=g) * (0.7 ** torch.arange(40, device=dev, dtype=torch.float64))
+        Cs = B @ B.transpose(1, 2) + 1e-6 * torch.eye(p, device=dev, dtype=torch.float64)
+        outs = []
+        for use_graph in (True, False, True):
+            engine.EIG_GRAPH = use_graph
+            try:
+                r0 = engine.graph_replayed_launches
+                outs.append(engine.eig_topk_subspace(Cs, k, tol=1e-12))
+                assert (engine.graph_replayed_launches > r0) == use_graph
+            finally:
+                engine.EIG_GRAPH = True
+        for a, b in ((outs[0], outs[1]), (outs[2], outs[1])):
+            for u, v in zip(a, b):
+                assert torch.equal(u, v)
+        assert bool(outs[0][3].all())
+        ev = torch.linalg.eigvalsh(Cs).flip(1)[:, :k]
+        np.testing.assert_allclose(outs[0][0][:, :k].cpu().numpy(), ev.cpu().numpy(), rtol=1e-10)
+
+
 def test_full_spectrum_solver(torch):
     """ocm_eigvals_sym_f64 (Householder tridiagonalisation + bisection) against numpy.linalg.eigvalsh: covariance-like
     matrices with a 1e-8 dynamic range, a rank-deficient one, tiny and odd sizes; absolute error a few ulp of |A|."""
