@@ -403,8 +403,9 @@ def test_subspace_eigensolver_kernels(torch):
 
 
 def test_subspace_iteration_graph_replay_equals_eager(torch):
-    """The subspace-iteration cycle replayed from its CUDA graph (engine._eig_graph) gives bit for bit what the eager
-    loop gives: batched (CV-fold shape) and single (fit shape), repeated calls on the cached graph included."""
+    """The subspace-iteration cycle replayed from its CUDA graph (engine._eig_graph, opt-in) gives what the eager loop
+    gives, to the rounding of the fp64-atomic Gram products: batched (CV-fold shape) and single (fit shape), repeated
+    calls on the cached graph included."""
     dev = torch.device("cuda")
     g = torch.Generator(device=dev); g.manual_seed(4)
     for F, p, k in ((4, 260, 20), (1, 512, 10)):
@@ -418,10 +419,12 @@ def test_subspace_iteration_graph_replay_equals_eager(torch):
                 outs.append(engine.eig_topk_subspace(Cs, k, tol=1e-12))
                 assert (engine.graph_replayed_launches > r0) == use_graph
             finally:
-                engine.EIG_GRAPH = True
+                engine.EIG_GRAPH = False
         for a, b in ((outs[0], outs[1]), (outs[2], outs[1])):
-            for u, v in zip(a, b):
-                assert torch.equal(u, v)
+            np.testing.assert_allclose(a[0][:, :k].cpu().numpy(), b[0][:, :k].cpu().numpy(), rtol=1e-11)
+            np.testing.assert_allclose(a[2].cpu().numpy(), b[2].cpu().numpy(), rtol=1e-8)
+            np.testing.assert_allclose(a[1][:, :, :k].cpu().numpy(), b[1][:, :, :k].cpu().numpy(), atol=1e-7)
+            assert torch.equal(a[3], b[3])
         assert bool(outs[0][3].all())
         ev = torch.linalg.eigvalsh(Cs).flip(1)[:, :k]
         np.testing.assert_allclose(outs[0][0][:, :k].cpu().numpy(), ev.cpu().numpy(), rtol=1e-10)
