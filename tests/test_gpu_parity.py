@@ -944,6 +944,46 @@ def test_host_buffer_api(torch):
     assert lib.ocm_simca_host_release() == 0 and lib.ocm_simca_host_release() == 0
 
 
+def test_host_buffer_api_fp64_rows(torch):
+    """ocm_simca_score_host_f64in on small and ragged inputs: fp64 rows centred on the host threads (bit-identical to the
+    device-side fp64 path), leading dimension, several chunk sizes, fused SNV, empty input."""
+    lib = native.lib()
+    dev = torch.device("cuda")
+    n, p, A = 3001, 260, 6
+    X = synth.make_spectra(n, p, seed=17) + 1e-9 * np.random.default_rng(3).standard_normal((n, p))
+    ref = so.fit_one_class(X[:800], A)
+    T2r, Qr = so.score(ref, X)
+    mu = np.ascontiguousarray(ref["pred_mean"], np.float64); P = np.ascontiguousarray(ref["pred_P"], np.float32)
+    S = np.ascontiguousarray(ref["Sinv"], np.float32)
+    prm = native.ScoreParams(A=A, rule=1, snv=0, snv_eps=1e-8, ct=1.0 / ref["T2_limit"], cq=1.0 / ref["Q_limit"], dlim=float(ref["D_limit"]))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    Xp = np.zeros((n, p + 6)); Xp[:, :p] = X
+    outs = []
+    for Xa, ld, chunk in ((X, p, 0), (X, p, 700), (Xp, p + 6, 1024)):
+        T2 = np.zeros(n, np.float32); Q = np.zeros(n, np.float32); acc = np.zeros(n, np.uint8)
+        native.check(lib.ocm_simca_score_host_f64in(vp(Xa), n, p, ld, vp(mu), vp(P), vp(S), C.byref(prm), chunk, vp(T2), vp(Q), vp(acc)))
+        outs.append((T2, Q, acc))
+    for T2, Q, acc in outs[1:]:
+        assert np.array_equal(T2, outs[0][0]) and np.array_equal(Q, outs[0][1]) and np.array_equal(acc, outs[0][2])
+    np.testing.assert_allclose(outs[0][0], T2r, rtol=RTOL, atol=2e-7 * A)
+    np.testing.assert_allclose(outs[0][1], Qr, rtol=RTOL)
+    # the device-side fp64 path rounds at the same point: identical bits
+    T2d, Qd, accd = engine.score(torch.as_tensor(X, device=dev), torch.as_tensor(mu, device=dev), torch.as_tensor(ref["pred_P"], device=dev),
+                                 torch.as_tensor(ref["Sinv"], device=dev), rule="alt", ct=1.0 / ref["T2_limit"], cq=1.0 / ref["Q_limit"],
+                                 dlim=float(ref["D_limit"]))
+    assert np.array_equal(T2d.cpu().numpy(), outs[0][0]) and np.array_equal(Qd.cpu().numpy(), outs[0][1])
+    # fused SNV on fp64 host rows
+    Xs = so.snv(X * 1.7 + 0.4)
+    refs = so.fit_one_class(Xs[:800], A)
+    T2s, Qs, _ = engine.score_host(X * 1.7 + 0.4, refs["pred_mean"], refs["pred_P"], refs["Sinv"], snv=True)
+    T2sr, Qsr = so.score(refs, Xs)
+    np.testing.assert_allclose(T2s, T2sr, rtol=2e-4, atol=4e-7 * A)
+    np.testing.assert_allclose(Qs, Qsr, rtol=2e-4)
+    assert lib.ocm_simca_score_host_f64in(vp(X), 0, p, p, vp(mu), vp(P), vp(S), C.byref(prm), 0, None, None, None) == 0
+    assert lib.ocm_simca_score_host_f64in(None, 5, p, p, vp(mu), vp(P), vp(S), C.byref(prm), 0, None, None, None) != 0
+    assert lib.ocm_simca_host_release() == 0
+
+
 def test_host_buffer_api_bulk_chunks_take_the_tensor_core_kernel(torch):
     """Host buffers with chunks large enough for the tcgen05 kernel, in its fp16 operand mode (x_rms given): every chunk
     is followed by its own fix-up scan; a row 1e6 times out of range must come back finite and rejected."""
