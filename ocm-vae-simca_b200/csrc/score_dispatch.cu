@@ -298,8 +298,11 @@ extern "C" int ocm_upload_rows(const void* h_src, int64_t n, int64_t row_bytes, 
         if (!w.ev_h2d[b]) OCM_TRY(cudaEventCreateWithFlags(&w.ev_h2d[b], cudaEventDisableTiming));
     }
     if (is_pinned(h_src)) {
-        OCM_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_stride, src, (size_t)src_stride, (size_t)row_bytes, (size_t)n,
-                                  cudaMemcpyHostToDevice, w.st[0]));
+        if (src_stride == row_bytes && dst_stride == row_bytes)
+            OCM_TRY(cudaMemcpyAsync(dst, src, (size_t)n * row_bytes, cudaMemcpyHostToDevice, w.st[0]));
+        else
+            OCM_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_stride, src, (size_t)src_stride, (size_t)row_bytes, (size_t)n,
+                                      cudaMemcpyHostToDevice, w.st[0]));
         OCM_TRY(cudaStreamSynchronize(w.st[0]));
         return 0;
     }
@@ -331,8 +334,11 @@ extern "C" int ocm_upload_rows(const void* h_src, int64_t n, int64_t row_bytes, 
         }
         work(0, per < m ? per : m);
         for (auto& t : th) t.join();
-        OCM_TRY(cudaMemcpy2DAsync(dst + r0 * dst_stride, (size_t)dst_stride, bounce, (size_t)row_bytes, (size_t)row_bytes, (size_t)m,
-                                  cudaMemcpyHostToDevice, w.st[b]));
+        if (dst_stride == row_bytes)      // dense destination: ONE 1-D copy (a 2-D copy of narrow rows runs at a third of the link)
+            OCM_TRY(cudaMemcpyAsync(dst + r0 * dst_stride, bounce, (size_t)m * row_bytes, cudaMemcpyHostToDevice, w.st[b]));
+        else
+            OCM_TRY(cudaMemcpy2DAsync(dst + r0 * dst_stride, (size_t)dst_stride, bounce, (size_t)row_bytes, (size_t)row_bytes, (size_t)m,
+                                      cudaMemcpyHostToDevice, w.st[b]));
         OCM_TRY(cudaEventRecord(w.ev_h2d[b], w.st[b]));
     }
     for (int k = 0; k < 2; ++k) OCM_TRY(cudaStreamSynchronize(w.st[k]));

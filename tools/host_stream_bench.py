@@ -41,3 +41,7 @@ out["pageable_f64"] = {"spectra_per_s": n / t, "host_read_GBs": 8.0 * p * n / t 
 t = timed(lambda: engine.score(torch.from_numpy(X64).to(dev), pca.mean, pca.P, Sinv, **kw))
 out["upload_whole_then_score_f64"] = {"spectra_per_s": n / t}
 print(json.dumps(out))
+# engine.to_device of a large numpy matrix (ocm_upload_rows) against torch's own pageable copy
+t = timed(lambda: engine.to_device(X32))
+print(json.dumps({"to_device_f32_GBs": X32.nbytes / t / 1e9, "torch_to_GBs": X32.nbytes / timed(lambda: torch.from_numpy(X32).to(dev)) / 1e9,
+                  "to_device_f64_GBs": X64.nbytes / timed(lambda: engine.to_device(X64)) / 1e9}))
