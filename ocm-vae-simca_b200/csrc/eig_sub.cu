@@ -42,23 +42,34 @@ symm_mul_kernel(const double* __restrict__ C, const double* __restrict__ Q, doub
     double acc[NT8][2];
 #pragma unroll
     for (int n = 0; n < NT8; ++n) acc[n][0] = acc[n][1] = 0.0;
-    for (int j0 = 0; j0 < p; j0 += SM_KC) {
-        // C tile: 64 x 32, 8 doubles per thread (row = tid / 4, 8 consecutive columns)
-        {
-            const int r = tid >> 2, c8 = (tid & 3) * 8;
-            const int i = i0 + r;
+    // The next chunk's global loads are issued into registers BEFORE the DMMAs of the current one (the first version
+    // loaded, synchronised, multiplied, synchronised: every chunk paid the full L2 latency; the solve of a CV grid spends a
+    // quarter of its time in this kernel).  C tile: 64 x 32, 8 doubles per thread (row = tid / 4, 8 consecutive columns);
+    // Q tile: 32 x (8 NT8), NT8 doubles per thread.
+    const int cr = tid >> 2, cc8 = (tid & 3) * 8, ci = i0 + cr;
+    constexpr int QPT = SM_KC * NT8 * 8 / 256;
+    double creg[8], qreg[QPT];
+    auto fetch = [&](int j0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = j0 + c8 + e;
-                Cs[r][c8 + e] = (i < p && j < p) ? Cf[(size_t)i * p + j] : 0.0;
-            }
+        for (int e = 0; e < 8; ++e) {
+            const int j = j0 + cc8 + e;
+            creg[e] = (ci < p && j < p) ? Cf[(size_t)ci * p + j] : 0.0;
         }
-        for (int idx = tid; idx < SM_KC * NT8 * 8; idx += 256) {
-            const int r = idx / (NT8 * 8), c = idx % (NT8 * 8);
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int idx = tid + 256 * u, r = idx / (NT8 * 8), c = idx % (NT8 * 8);
             const int j = j0 + r;
-            Qs[r][c] = (j < p && c < kb) ? Qf[(size_t)j * kb + c] : 0.0;
+            qreg[u] = (j < p && c < kb) ? Qf[(size_t)j * kb + c] : 0.0;
         }
+    };
+    fetch(0);
+    for (int j0 = 0; j0 < p; j0 += SM_KC) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Cs[cr][cc8 + e] = creg[e];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) { const int idx = tid + 256 * u; Qs[idx / (NT8 * 8)][idx % (NT8 * 8)] = qreg[u]; }
         __syncthreads();
+        if (j0 + SM_KC < p) fetch(j0 + SM_KC);
 #pragma unroll
         for (int k4 = 0; k4 < SM_KC / 4; ++k4) {
             const double a = Cs[8 * warp + g][4 * k4 + tq];
