@@ -207,6 +207,13 @@ int ocm_simca_score_snv_staged_f32(const float* X, int64_t n, int32_t p, int64_t
                                    const float* mu, const float* P, const float* Sinv,
                                    const ocm_score_params* h_params,
                                    float* T2, float* Q, uint8_t* accept, void* stream);
+/* Raw spectra -> distances and decisions in one call: [row SNV +] Savitzky-Golay filter (the arguments of ocm_savgol_f32)
+ * into a bounded scratch chunk, then the bulk scoring kernels against a model fitted in the filtered space
+ * (simca_nuts.py:48-52 followed by utils/SIMCA.py:120-154, without the second full-size matrix).  h_params->snv must be 0. */
+int ocm_simca_score_savgol_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_t snv, float snv_eps,
+                               const float* h_coef, int32_t window, const float* edge_l, const float* edge_r,
+                               const float* mu, const float* P, const float* Sinv, const ocm_score_params* h_params,
+                               float* T2, float* Q, uint8_t* accept, void* stream);
 /* the fp64 contract above, forced onto the generic kernel */
 int ocm_simca_score_simt_f64in(const double* X, int64_t n, int32_t p, int64_t ldx,
                                const double* mu, const float* P, const float* Sinv,

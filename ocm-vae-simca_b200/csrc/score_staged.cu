@@ -107,11 +107,12 @@ int scratch_pool(cudaMemPool_t* out) {
     return 0;
 }
 
-// Scores n rows chunk by chunk: `fill(first_row, rows, scratch)` launches the kernel that writes the centred fp32 rows
-// [rows][p] of the chunk, the bulk dispatcher scores them against a zero mean.
+// Scores n rows chunk by chunk: `fill(first_row, rows, scratch)` launches the kernel that writes the fp32 rows [rows][p]
+// of the chunk -- already centred (mu == nullptr: the bulk dispatcher then scores against a zero mean) or preprocessed
+// but not centred (mu = the model mean).
 template <typename Fill>
 int score_chunks(int64_t n, int32_t p, const float* P, const float* Sinv, const ocm_score_params* hp,
-                 float* T2, float* Q, uint8_t* accept, void* stream, Fill fill) {
+                 float* T2, float* Q, uint8_t* accept, void* stream, Fill fill, const float* mu = nullptr) {
     cudaStream_t st = (cudaStream_t)stream;
     int64_t chunk = scratch_bytes() / (4 * (int64_t)p);
     if (chunk < kMinBulkRows) chunk = kMinBulkRows;
@@ -135,7 +136,7 @@ int score_chunks(int64_t n, int32_t p, const float* P, const float* Sinv, const 
         const int64_t m = (n - r0 < chunk + kMinBulkRows) ? n - r0 : chunk;      // no tail below the bulk gate
         rc = fill(r0, m, xc);
         if (rc == 0)
-            rc = ocm_simca_score_f32(xc, m, p, p, zero_mu, P, Sinv, &prm, T2 ? T2 + r0 : nullptr, Q ? Q + r0 : nullptr,
+            rc = ocm_simca_score_f32(xc, m, p, p, mu ? mu : zero_mu, P, Sinv, &prm, T2 ? T2 + r0 : nullptr, Q ? Q + r0 : nullptr,
                                      accept ? accept + r0 : nullptr, nullptr, stream);
         r0 += m;
     }
@@ -208,5 +209,25 @@ extern "C" int ocm_simca_score_snv_staged_f32(const float* X, int64_t n, int32_t
         return ocm_preprocess_f32(X + r0 * ldx, m, p, ldx, OCM_PRE_SNV_CENTER, mu, nullptr, eps, xc, p, stream);
     });
     if (rc == kNoScratch) return ocm_simca_score_simt_f32(X, n, p, ldx, mu, P, Sinv, hp, T2, Q, accept, nullptr, stream);
+    return rc;
+}
+
+// Raw spectra -> decisions in one call: [SNV +] Savitzky-Golay (ocm_savgol_f32: simca_nuts.py:48-52,
+// utils/data_utils.py:57-59) into the scratch chunk, then the bulk dispatcher against the model (whose mean lives in the
+// preprocessed space).  What the reference's drivers do as three numpy passes and a second full-size matrix.
+extern "C" int ocm_simca_score_savgol_f32(const float* X, int64_t n, int32_t p, int64_t ldx, int32_t snv, float snv_eps,
+                                          const float* h_coef, int32_t window, const float* edge_l, const float* edge_r,
+                                          const float* mu, const float* P, const float* Sinv, const ocm_score_params* hp,
+                                          float* T2, float* Q, uint8_t* accept, void* stream) {
+    using namespace ocm;
+    using namespace ocm::staged;
+    if (n == 0) return 0;
+    OCM_REQUIRE(X && mu && P && Sinv && hp && h_coef && edge_l && edge_r, OCM_EINVAL, "NULL buffer");
+    OCM_REQUIRE(hp->snv == 0, OCM_EINVAL, "row SNV goes in front of the filter (the snv argument), not behind it");
+    OCM_REQUIRE(n > 0 && p > 0 && ldx >= p, OCM_EINVAL, "bad shape");
+    const int rc = score_chunks(n, p, P, Sinv, hp, T2, Q, accept, stream, [&](int64_t r0, int64_t m, float* xc) {
+        return ocm_savgol_f32(X + r0 * ldx, m, p, ldx, snv, snv_eps, h_coef, window, edge_l, edge_r, xc, p, stream);
+    }, mu);
+    if (rc == kNoScratch) { set_error("ocm_simca_score_savgol_f32: no scratch memory for the filtered chunk"); return (int)cudaErrorMemoryAllocation; }
     return rc;
 }

@@ -735,6 +735,36 @@ def score(X, mean, P, Sinv, rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), snv=Fal
     return (T2, Q, acc, sc) if want_scores else (T2, Q, acc)
 
 
+def score_savgol(X, mean, P, Sinv, window_length=5, polyorder=2, deriv=1, delta=1.0, pre_snv=True, snv_eps=1e-8,
+                 rule="alt", ct=1.0, cq=1.0, dlim=np.sqrt(2), x_rms=0.0):
+    """Raw fp32 device rows -> (T2, Q, accept) against a model fitted on [SNV +] Savitzky-Golay filtered spectra
+    (ocm_simca_score_savgol_f32): the filter runs chunk by chunk into a bounded scratch, the filtered matrix is never
+    materialised.  Same numbers as `score(savgol(X, ..., snv=pre_snv), ...)`."""
+    torch = _torch()
+    X = to_device(X, dtype=torch.float32)
+    n, p = X.shape
+    A = P.shape[0]
+    dev = X.device
+    key = (int(window_length), int(polyorder), int(deriv), float(delta), str(dev))
+    if key not in _SG_DEVICE:
+        g, el, er = _savgol_tables(int(window_length), int(polyorder), int(deriv), delta)
+        _SG_DEVICE[key] = (g, torch.as_tensor(el, device=dev).contiguous(), torch.as_tensor(er, device=dev).contiguous())
+    g, el_d, er_d = _SG_DEVICE[key]
+    T2 = torch.empty(n, dtype=torch.float32, device=dev)
+    Q = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = torch.empty(n, dtype=torch.uint8, device=dev)
+    prm = native.ScoreParams(A=A, rule=RULES[rule] if isinstance(rule, str) else int(rule), snv=0, snv_eps=float(snv_eps),
+                             ct=float(ct), cq=float(cq), dlim=float(dlim), x_rms=float(x_rms or 0.0))
+    mu = mean.to(device=dev, dtype=torch.float32).contiguous()
+    P32 = P.to(device=dev, dtype=torch.float32).contiguous()
+    S32 = Sinv.to(device=dev, dtype=torch.float32).contiguous()
+    rc = native.lib().ocm_simca_score_savgol_f32(_p(X), n, p, X.stride(0), int(bool(pre_snv)), float(snv_eps),
+                                                 g.ctypes.data_as(C.c_void_p), int(window_length), _p(el_d), _p(er_d),
+                                                 _p(mu), _p(P32), _p(S32), C.byref(prm), _p(T2), _p(Q), _p(acc), _stream())
+    native.check(rc, "ocm_simca_score_savgol_f32")
+    return T2, Q, acc
+
+
 HOST_STREAM_BYTES = 256 << 20      # host matrices above this are streamed through the host-buffer call, not uploaded whole
 
 

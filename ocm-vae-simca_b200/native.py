@@ -135,6 +135,8 @@ SIGNATURES = {
     "ocm_simca_score_snv_staged_supported": (C.c_int, [_i64, _i32, _i64, _i32, _vp, _vp]),
     "ocm_simca_score_snv_staged_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, C.POINTER(ScoreParams),
                                                  _vp, _vp, _vp, _vp]),
+    "ocm_simca_score_savgol_f32": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
+                                             C.POINTER(ScoreParams), _vp, _vp, _vp, _vp]),
     "ocm_simca_score_f64in_bulk_supported": (C.c_int, [_i64, _i32, _i64, _i32, _vp, _vp]),
     "ocm_simca_score_multiA_f32": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _f32,
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -611,6 +611,43 @@ def test_fused_snv_wide_spectra_are_staged(torch):
         assert float(((Q - outs[1][1]).abs() / outs[1][1]).max()) < 5e-4, msg
 
 
+def test_raw_spectra_to_decisions_in_one_call(torch):
+    """engine.score_savgol (SNV + Savitzky-Golay staged chunk by chunk in front of the bulk kernels; simca_nuts.py:48-52 +
+    utils/SIMCA.py:120-154) equals filtering the whole matrix first and scoring it, bit for bit, across scratch chunks;
+    and matches scipy + the fp64 arithmetic."""
+    from scipy.signal import savgol_filter
+    dev = torch.device("cuda")
+    n, p, A = 100_003, 1024, 8
+    X = synth.make_spectra_device(n, p, dev, seed=12)
+    g = torch.Generator(device=dev); g.manual_seed(9)
+    X = X * (1.0 + 0.2 * torch.rand(n, 1, device=dev, generator=g)) + 0.3 * torch.rand(n, 1, device=dev, generator=g)
+    Xp = engine.savgol(X, 5, 2, 1, snv=True)
+    pca = engine.fit_pca(Xp[:4000].contiguous(), None, A)
+    Sinv = torch.diag(torch.as_tensor(1.0 / pca.eigs_all[:A], device=dev))
+    kw = dict(rule="alt", ct=0.05, cq=50.0, dlim=np.sqrt(2), x_rms=pca.x_rms)
+    T2a, Qa, acca = engine.score(Xp, pca.mean, pca.P, Sinv, **kw)
+    os.environ["OCM_STAGED_SCRATCH_MB"] = "160"          # 40 960 rows per chunk: two chunks, the second takes the ragged tail
+    try:
+        T2b, Qb, accb = engine.score_savgol(X, pca.mean, pca.P, Sinv, 5, 2, 1, pre_snv=True, **kw)
+    finally:
+        del os.environ["OCM_STAGED_SCRATCH_MB"]
+    assert torch.equal(T2a, T2b) and torch.equal(Qa, Qb) and torch.equal(acca, accb)
+    sub = slice(None, None, 97)
+    Xh = X[sub].double().cpu().numpy()
+    Xs = so.snv(Xh)
+    Xf = savgol_filter(Xs, 5, 2, deriv=1, axis=1, mode="interp")
+    model = dict(pred_mean=pca.mean.cpu().numpy(), pred_P=pca.P.cpu().numpy(), Sinv=Sinv.cpu().numpy())
+    T2r, Qr = so.score(model, Xf)
+    # fp32 SNV + filter in front of the model (f1: 3e-5 of the row scale, amplified by 1 / lambda_A): the exact check is
+    # the bitwise one above, this one says the pipeline is the reference's pipeline
+    assert float(np.median(np.abs(T2b[sub].cpu().numpy() - T2r) / T2r)) < 5e-3
+    assert float(np.median(np.abs(Qb[sub].cpu().numpy() - Qr) / Qr)) < 5e-3
+    # small input: one chunk, generic kernel
+    T2s, Qs, _ = engine.score_savgol(X[:300], pca.mean, pca.P, Sinv, 5, 2, 1, pre_snv=True, **kw)
+    T2t, Qt, _ = engine.score(Xp[:300].contiguous(), pca.mean, pca.P, Sinv, **kw)
+    assert torch.equal(T2s, T2t) and torch.equal(Qs, Qt)
+
+
 def test_fp64_rows_take_the_bulk_path(torch):
     """fp64 spectra (numpy's default, what utils/SIMCA.py:127 receives) at bulk shapes: centred / SNV-normalised in fp64,
     rounded once, scored on the tcgen05 kernels chunk by chunk -- against the fp64 arithmetic and the generic kernel;
