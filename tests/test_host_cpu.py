@@ -259,3 +259,20 @@ def test_convvae_channels_last_mode_is_the_same_network():
     np.testing.assert_allclose(rb[0].numpy(), ra[0].numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(rb[1].numpy(), ra[1].numpy(), rtol=1e-4, atol=1e-5)
     assert set(a.state_dict()) == set(b.state_dict())
+
+
+def test_host_streamable_gate():
+    """engine.host_streamable: which host matrices SIMCA.predict / transform stream through the host-buffer call
+    instead of uploading whole (shape / dtype / stride logic only; no device needed)."""
+    from ocm_vae_simca_b200 import engine
+    big = np.zeros((70_000, 1024), np.float32)                    # 287 MB > HOST_STREAM_BYTES
+    assert big.nbytes > engine.HOST_STREAM_BYTES and engine.host_streamable(big)
+    assert engine.host_streamable(np.zeros((40_000, 1024), np.float64))
+    assert engine.host_streamable(np.zeros((70_000, 1100), np.float32)[:, :1024])      # row stride > p: fine
+    assert not engine.host_streamable(big[:1000])                                      # small: one upload, one launch
+    assert not engine.host_streamable(big.astype(np.float16))
+    assert not engine.host_streamable(np.asfortranarray(big))                          # column-major
+    assert not engine.host_streamable(big[:, ::2])                                     # strided columns
+    assert not engine.host_streamable(big.reshape(70_000, 32, 32))
+    assert not engine.host_streamable(big.tolist()[:2])
+    assert not engine.host_streamable(np.zeros((0, 1024), np.float32))
