@@ -24,6 +24,7 @@ jacobi_eigh_kernel(const double* __restrict__ Hin, int m, double* __restrict__ e
     __shared__ int pp[JMAX / 2], qq[JMAX / 2];
     __shared__ int order[JMAX];
     __shared__ double s_off, s_diag;
+    __shared__ double red[8][2];
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* H = Hin + (size_t)blockIdx.x * m * m;
     const int me = (m + 1) & ~1;               // even size for the tournament (a dummy index when m is odd)
@@ -34,13 +35,24 @@ jacobi_eigh_kernel(const double* __restrict__ Hin, int m, double* __restrict__ e
     }
     __syncthreads();
     for (int sweep = 0; sweep < 30; ++sweep) {
-        if (tid == 0) {
+        {
+            // off-diagonal and diagonal mass, all threads (one thread walking the m^2 / 2 entries cost ~10 us per sweep,
+            // a quarter of the kernel at m = 32)
             double off = 0.0, dg = 0.0;
-            for (int r = 0; r < m; ++r) {
-                dg += A_AT(r, r) * A_AT(r, r);
-                for (int c = r + 1; c < m; ++c) off += A_AT(r, c) * A_AT(r, c);
+            for (int i = tid; i < m * m; i += nt) {
+                const int r = i / m, c = i % m;
+                const double v = A_AT(r, c);
+                if (c > r) off = fma(v, v, off);
+                else if (c == r) dg = fma(v, v, dg);
             }
-            s_off = off; s_diag = dg;
+            off = warp_sum(off); dg = warp_sum(dg);
+            if ((tid & 31) == 0) { red[tid >> 5][0] = off; red[tid >> 5][1] = dg; }
+            __syncthreads();
+            if (tid == 0) {
+                double o = 0.0, d = 0.0;
+                for (int w = 0; w < (nt >> 5); ++w) { o += red[w][0]; d += red[w][1]; }
+                s_off = o; s_diag = d;
+            }
         }
         __syncthreads();
         if (s_off <= 1e-30 * s_diag || s_off == 0.0) break;
@@ -93,14 +105,19 @@ jacobi_eigh_kernel(const double* __restrict__ Hin, int m, double* __restrict__ e
             __syncthreads();
         }
     }
-    // descending order (selection sort on m <= 64 values by one thread)
-    if (tid == 0) {
-        for (int i = 0; i < m; ++i) order[i] = i;
-        for (int i = 0; i < m; ++i) {
-            int best = i;
-            for (int j = i + 1; j < m; ++j) if (A_AT(order[j], order[j]) > A_AT(order[best], order[best])) best = j;
-            const int t = order[i]; order[i] = order[best]; order[best] = t;
+    // descending order by counting: the rank of eigenvalue i is the number of larger ones (ties: the lower index first)
+    if (tid < m) {
+        const double di = A_AT(tid, tid);
+        int rank = 0;
+        const bool ni = di != di;
+        for (int j = 0; j < m; ++j) {
+            const double dj = A_AT(j, j);
+            const bool nj = dj != dj;
+            // a total order (NaNs last, ties by index): the ranks are a permutation whatever the matrix held
+            const bool before = (nj || ni) ? ((!nj && ni) || (nj == ni && j < tid)) : (dj > di || (dj == di && j < tid));
+            rank += before ? 1 : 0;
         }
+        order[rank] = tid;
     }
     __syncthreads();
     double* w = evals + (size_t)blockIdx.x * m;
