@@ -94,6 +94,24 @@ int fill_threads() {
     return (int)(t < 1 ? 1 : (t > 64 ? 64 : t));
 }
 
+// work(r0, r1) over [0, m) in `nt` contiguous ranges, one per thread (the caller's thread takes the first).  A thread that
+// cannot be started (resource limits) does not take the process down: its range is done inline.
+template <typename Work>
+void parallel_ranges(int64_t m, int nt, Work work) {
+    if (nt > m) nt = (int)(m > 0 ? m : 1);
+    if (nt <= 1) { work((int64_t)0, m); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    const int64_t per = (m + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t r0 = t * per, r1 = (r0 + per < m) ? r0 + per : m;
+        if (r0 >= r1) continue;
+        try { th.emplace_back(work, r0, r1); } catch (...) { work(r0, r1); }
+    }
+    work((int64_t)0, per < m ? per : m);
+    for (auto& t : th) t.join();
+}
+
 // rows [0, m) of the caller's matrix -> dense fp32 rows [m][p] in a pinned buffer, on `nt` threads (row ranges)
 template <typename TIn>
 void fill_rows(float* dst, const TIn* src, int64_t m, int32_t p, int64_t ldx, const double* mu_or_null, int nt) {
@@ -113,17 +131,7 @@ void fill_rows(float* dst, const TIn* src, int64_t m, int32_t p, int64_t ldx, co
             }
         }
     };
-    if (nt > m) nt = (int)(m > 0 ? m : 1);
-    if (nt <= 1) { work(0, m); return; }
-    std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    const int64_t per = (m + nt - 1) / nt;
-    for (int t = 1; t < nt; ++t) {
-        const int64_t r0 = t * per, r1 = (r0 + per < m) ? r0 + per : m;
-        if (r0 < r1) th.emplace_back(work, r0, r1);
-    }
-    work(0, per < m ? per : m);
-    for (auto& t : th) t.join();
+    parallel_ranges(m, nt, work);
 }
 
 template <typename TIn>
@@ -324,16 +332,7 @@ extern "C" int ocm_upload_rows(const void* h_src, int64_t n, int64_t row_bytes, 
             if (src_stride == row_bytes) { memcpy(bounce + a0 * row_bytes, src + (r0 + a0) * src_stride, (size_t)(a1 - a0) * row_bytes); return; }
             for (int64_t r = a0; r < a1; ++r) memcpy(bounce + r * row_bytes, src + (r0 + r) * src_stride, (size_t)row_bytes);
         };
-        int t_use = nt > m ? (int)m : nt;
-        if ((int64_t)m * row_bytes < (4 << 20)) t_use = 1;
-        const int64_t per = (m + t_use - 1) / t_use;
-        std::vector<std::thread> th;
-        for (int t = 1; t < t_use; ++t) {
-            const int64_t a0 = t * per, a1 = (a0 + per < m) ? a0 + per : m;
-            if (a0 < a1) th.emplace_back(work, a0, a1);
-        }
-        work(0, per < m ? per : m);
-        for (auto& t : th) t.join();
+        parallel_ranges(m, (int64_t)m * row_bytes < (4 << 20) ? 1 : nt, work);
         if (dst_stride == row_bytes)      // dense destination: ONE 1-D copy (a 2-D copy of narrow rows runs at a third of the link)
             OCM_TRY(cudaMemcpyAsync(dst + r0 * dst_stride, bounce, (size_t)m * row_bytes, cudaMemcpyHostToDevice, w.st[b]));
         else
