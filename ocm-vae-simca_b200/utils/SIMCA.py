@@ -279,12 +279,30 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         return engine.score_host(X, info["_pca"].mean, info["_pca"].P, info["_Sinv"], rule=self.type,
                                  ct=ct, cq=cq, dlim=lim.D_limit, snv=snv, x_rms=getattr(info["_pca"], "x_rms", 0.0))
 
+    def _score_all_classes_host(self, X):
+        """[(T2, Q, accept)] per model class for a large host matrix.  One class: the overlapped host-buffer call.
+        Several classes: every chunk crosses the link ONCE (engine.to_device: pinned bounce buffers) and is scored
+        against each class while it is on the device."""
+        if len(self.model_class) == 1:
+            return [self._score_class_host(X, self.model_class[0])]
+        n = X.shape[0]
+        outs = [(np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8)) for _ in self.model_class]
+        rows = max(65536, engine.HOST_STREAM_BYTES // max(1, X.strides[0]))
+        rows = -(-n // -(-n // rows))                      # equal chunks, none below the bulk kernels' row gate
+        for r0 in range(0, n, rows):
+            Xd = engine.to_device(X[r0:r0 + rows])
+            for k, cls in enumerate(self.model_class):
+                T2, Q, acc = self._score_class(Xd, cls)
+                for dst, src in zip(outs[k], (T2, Q, acc)):
+                    dst[r0:r0 + rows] = src.cpu().numpy()
+        return outs
+
     def transform(self, X):
         """(T2, T2red, Q, Qred) of the LAST model class, as the reference returns (SIMCA.py:101-117)."""
         if engine.host_streamable(X):
-            for cls in self.model_class:
-                T2, Q, _ = self._score_class_host(X, cls)
-                ct, cq = self._model[cls]["_limits"].reduced_scales(self.type)
+            cls = self.model_class[-1]                     # the reference's loop overwrites: only the last class comes back
+            T2, Q, _ = self._score_class_host(X, cls)
+            ct, cq = self._model[cls]["_limits"].reduced_scales(self.type)
             T2h, Qh = T2.astype(np.float64), Q.astype(np.float64)
             return T2h, T2h * ct, Qh, Qh * cq
         on_device = _is_cuda_tensor(X)
@@ -306,8 +324,8 @@ class SIMCA(BaseEstimator, ClassifierMixin):
         if engine.host_streamable(X):
             # a large numpy matrix is streamed over the link (never resident as a whole); decisions come back per class
             predictions = out = np.empty((X.shape[0], len(self.model_class)), dtype=np.float64)
-            for i, cls in enumerate(self.model_class):
-                out[:, i] = self._score_class_host(X, cls)[2]
+            for i, (_, _, acc) in enumerate(self._score_all_classes_host(X)):
+                out[:, i] = acc
         else:
             Xd = engine.to_device(X)
             torch = engine._torch()

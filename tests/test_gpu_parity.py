@@ -1074,6 +1074,14 @@ def test_large_numpy_matrices_are_streamed(torch):
         np.testing.assert_allclose(T2h[sub], T2r, rtol=RTOL, atol=2e-7 * A)
         np.testing.assert_allclose(Qh[sub], Qr, rtol=RTOL)
         del Xd
+    # several model classes: every chunk crosses the link once and is scored against each class on the device
+    both = SIMCA(n_components=A, model_class=None, verbose=False).fit(X32[::20], y[::20])
+    assert len(both.model_class) == 2
+    ph = both.predict(X32)
+    pd_ = both.predict(torch.as_tensor(X32, device=dev)).cpu().numpy()
+    assert ph.shape == (n, 2) and np.array_equal(ph, pd_)
+    th, td = both.transform(X32), both.transform(torch.as_tensor(X32, device=dev))
+    assert np.array_equal(th[0], td[0].double().cpu().numpy()) and np.array_equal(th[2], td[2].double().cpu().numpy())
     # engine.to_device of a large numpy matrix goes through the same bounce buffers (ocm_upload_rows): exact copies
     Xpad = np.zeros((30_000, 1100), np.float32); Xpad[:, :1024] = X32[:30_000]
     for a in (X32, X32[:20_000].astype(np.float64), Xpad[:, :1024], X32[:17_000, :700]):
