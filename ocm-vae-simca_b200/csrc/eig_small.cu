@@ -76,27 +76,36 @@ jacobi_eigh_kernel(const double* __restrict__ Hin, int m, double* __restrict__ e
                 cs[tid][0] = c; cs[tid][1] = s;
             }
             __syncthreads();
-            // rows: A <- J^T A
-            for (int i = tid; i < (me / 2) * m; i += nt) {
-                const int k = i / m, col = i % m;
-                const int a = pp[k], b = qq[k];
-                if (b < m) {
-                    const double c = cs[k][0], s = cs[k][1];
-                    const double x = A_AT(a, col), y = A_AT(b, col);
-                    A_AT(a, col) = c * x - s * y;
-                    A_AT(b, col) = s * x + c * y;
+            // A <- J^T A J block by block: the 2 x 2 block (rows of pair k) x (columns of pair l) only needs the rotations
+            // of its own two pairs, so the row and the column rotations go in ONE pass (same operations in the same order
+            // as rows-then-columns, one barrier and one round trip through shared memory less per step)
+            const int np = me / 2;
+            for (int i = tid; i < np * np; i += nt) {
+                const int k = i / np, l = i % np;
+                const int a = pp[k], b = qq[k], e = pp[l], f = qq[l];
+                const bool rk = b < m, cl = f < m;                      // a dummy partner (odd m): that rotation is the identity
+                const double ck = cs[k][0], sk = cs[k][1], c2 = cs[l][0], s2 = cs[l][1];
+                double x00 = A_AT(a, e), x01 = cl ? A_AT(a, f) : 0.0;
+                double x10 = rk ? A_AT(b, e) : 0.0, x11 = (rk && cl) ? A_AT(b, f) : 0.0;
+                if (rk) {                                                // rows: (a, b) <- (c a - s b, s a + c b)
+                    const double t0 = ck * x00 - sk * x10, t1 = sk * x00 + ck * x10; x00 = t0; x10 = t1;
+                    const double u0 = ck * x01 - sk * x11, u1 = sk * x01 + ck * x11; x01 = u0; x11 = u1;
                 }
+                if (cl) {                                                // columns
+                    const double t0 = c2 * x00 - s2 * x01, t1 = s2 * x00 + c2 * x01; x00 = t0; x01 = t1;
+                    const double u0 = c2 * x10 - s2 * x11, u1 = s2 * x10 + c2 * x11; x10 = u0; x11 = u1;
+                }
+                A_AT(a, e) = x00;
+                if (cl) A_AT(a, f) = x01;
+                if (rk) A_AT(b, e) = x10;
+                if (rk && cl) A_AT(b, f) = x11;
             }
-            __syncthreads();
-            // columns: A <- A J, V <- V J
-            for (int i = tid; i < (me / 2) * m; i += nt) {
+            // V <- V J
+            for (int i = tid; i < np * m; i += nt) {
                 const int k = i / m, row = i % m;
                 const int a = pp[k], b = qq[k];
                 if (b < m) {
                     const double c = cs[k][0], s = cs[k][1];
-                    const double x = A_AT(row, a), y = A_AT(row, b);
-                    A_AT(row, a) = c * x - s * y;
-                    A_AT(row, b) = s * x + c * y;
                     const double vx = V_AT(row, a), vy = V_AT(row, b);
                     V_AT(row, a) = c * vx - s * vy;
                     V_AT(row, b) = s * vx + c * vy;
