@@ -276,3 +276,23 @@ def test_host_streamable_gate():
     assert not engine.host_streamable(big.reshape(70_000, 32, 32))
     assert not engine.host_streamable(big.tolist()[:2])
     assert not engine.host_streamable(np.zeros((0, 1024), np.float32))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): ONE JSON line with the GPU arm's
+    metric / unit / config, `impl: reference`, a cpu_baseline describing the run and an e2e with no device traffic.
+    Needs no GPU; one bounded step."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "spectra scored/s (fused T2+Q)" and d["unit"] == "spectra/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert "10000000 x 1024" in d["config"]["workload"] and d["dtype"] == "f32"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
